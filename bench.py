@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the supersurfel hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" is one RGB-D frame through the whole path (segmentation -> supersurfel
+extraction -> frame-to-model ICP -> fusion/cull).  N=1 workload: BASELINE.json configs[1],
+a TUM-fr1/desk-shaped synthetic 640x480 sequence, full track+fuse.  N>1: N independent
+sequences (configs[3]), one process and one engine per GPU, no data-path collective
+("weak" scaling); the only collectives are the timing barrier and the max-over-ranks.
+
+Rank 0 prints ONE JSON line:
+  value     frames/s with the frames already resident in HBM (ssf_process_frame_device)
+  e2e       frames/s through the C-ABI call a reference user makes (ssf_process_frame) with
+            pinned HOST buffers: the H2D copy of the frame and the D2H read of the
+            pose/stats are inside the timed region
+  roofline  the ICP system kernel (the metric kernel) at HBM-bound sizing: 16 Mi source
+            supersurfels vs a 2560x1920 frame, algorithmic 72 B per supersurfel
+  cpu_baseline  the CPU oracle port of the same path on this box's host cores, bounded sample
+`--impl reference` times that CPU oracle port alone (the reference has no CPU
+implementation of this path and its full build needs ROS/OpenCV-CUDA/g2o).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "configs[1]: TUM-fr1/desk-shaped synthetic 640x480 RGB-D sequence, full track+fuse"
+PARAMS = dict(cell_size=16, lambda_pos=10.0, lambda_bound=1000.0, lambda_size=1000.0, lambda_disp=1e8,
+              thresh_disp=1e-4, seg_iter=10, seg_use_ransac=True, nb_samples=16, filter_iter=3, filter_alpha=0.1,
+              filter_beta=1.0, filter_threshold=0.05, range_min=0.2, range_max=5.0, delta_t=20, conf_thresh=2560.0,
+              nb_supersurfels_max=100000, icp_iter=10, icp_cov_thresh=0.05)   # launch/supersurfel_fusion_rgbd_benchmark.launch
+N_UNIQUE_FRAMES = 24
+ICP_BYTES_PER_SRC = 72
+ICP_ROOFLINE_N = 16 * 1024 * 1024
+
+
+def frame_index(step):
+    """Ping-pong over the rendered frames so that inter-frame motion stays ~1 cm."""
+    period = 2 * (N_UNIQUE_FRAMES - 1)
+    k = step % period
+    return k if k < N_UNIQUE_FRAMES else period - k
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def render_frames(seed):
+    from supersurfel_fusion_b200.synth import SyntheticSequence
+    seq = SyntheticSequence(width=640, height=480, seed=seed)
+    frames = [seq.frame(k) for k in range(N_UNIQUE_FRAMES)]
+    return seq, frames
+
+
+def time_cpu_oracle(frames, cam, n_frames):
+    """CPU oracle port on the host cores (single thread), bounded sample of the same workload."""
+    from oracle import orc
+    p = dict(PARAMS)
+    p["seg_use_ransac"] = int(p["seg_use_ransac"])
+    cfg = orc.default_config(cam=cam, **p)
+    orc.set_num_threads(1)
+    eng = orc.Engine(cfg)
+    eng.process_frame(*frames[0])         # bootstrap frame outside the timed region
+    t0 = time.perf_counter()
+    for s in range(1, n_frames + 1):
+        eng.process_frame(*frames[frame_index(s)])
+    dt = time.perf_counter() - t0
+    return n_frames / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    seq, frames = render_frames(1234)
+    steps = min(args.steps, 150)
+    # warm-up then K bounded steps, all on the host
+    fps, dt = time_cpu_oracle(frames, seq.cam_param(), args.warmup + steps)
+    line = {
+        "impl": "reference", "metric": "RGB-D frames/sec @640x480", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1000.0 / fps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "the reference has no CPU implementation of this path; this is the "
+                   "CPU oracle restatement of it (oracle/), single thread"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                         "sample": "%d frames of the workload sequence" % (args.warmup + steps)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def icp_roofline(device, peaks):
+    """ICP system kernel at HBM-bound sizing; returns the roofline object."""
+    import torch
+    from supersurfel_fusion_b200 import CamParam, SupersurfelFusion, Supersurfels
+    from supersurfel_fusion_b200.synth import synthetic_icp_problem
+    n = ICP_ROOFLINE_N
+    prob = synthetic_icp_problem(n, width=2560, height=1920, seed=1234)
+    eng = SupersurfelFusion(device).initialize(CamParam(*prob["cam"]), nb_supersurfels_max=n)
+    S = prob["S"]
+    frame = Supersurfels(S)
+    frame.colors[:] = prob["tgt_col"]; frame.orientations[:] = prob["tgt_ori"]; frame.confidences[:] = prob["tgt_conf"]
+    eng.setSegmentation(labels=prob["labels"], slanted=prob["depth"])
+    eng.setFrame(frame)
+    # model arrays straight from numpy (only the members the kernel reads are uploaded)
+    from supersurfel_fusion_b200.engine import SsfSurfels, _ptr
+    view = SsfSurfels(_ptr(prob["src_pos"]), _ptr(prob["src_col"]), None, _ptr(prob["src_ori"]), None, None, None)
+    eng.setModelPointers(view, n, n)
+    R = np.eye(3, dtype=np.float32)
+    t = np.array([0.002, -0.001, 0.003], np.float32)
+    sys29 = eng.icpSystem(R, t, n)                  # warm-up + sanity
+    for _ in range(3):
+        eng.icpSystemEnqueue(R, t, n, 1)
+    eng.synchronize()
+    L = 20
+    eng.timerStart()
+    eng.icpSystemEnqueue(R, t, n, L)                # 604 MB streamed per launch >> 126 MB L2: no flush needed
+    ms = eng.timerStop() / L
+    achieved = n * ICP_BYTES_PER_SRC / (ms * 1e-3) / 1e9
+    peak = peaks.get("hbm_gbs", 6650.0)
+    out = {"bound": "hbm", "kernel": "icp_system_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+           "frac": achieved / peak, "traffic": None,
+           "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+           "n_src": n, "us_per_launch": ms * 1e3, "algorithmic_bytes_per_src": ICP_BYTES_PER_SRC,
+           "streamed_only_gbs": n * 36 / (ms * 1e-3) / 1e9, "inlier_frac": float(sys29[28]) / n}
+    # latency at realistic sizes (L2 resident, launch bound): microseconds per system build
+    lat = {}
+    for m in (1200, 5000, 50000, 100000):
+        for _ in range(3):
+            eng.icpSystemEnqueue(R, t, m, 1)
+        eng.synchronize()
+        eng.timerStart()
+        eng.icpSystemEnqueue(R, t, m, 50)
+        lat[str(m)] = eng.timerStop() / 50 * 1e3
+    out["latency_us"] = lat
+    eng.close()
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from supersurfel_fusion_b200 import CamParam, SupersurfelFusion
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    seq, frames = render_frames(1234 + rank)       # configs[3]: independent sequences, seeds 1234..
+    cam = seq.cam_param()
+    # resident copies (value) and pinned host copies (e2e)
+    d_rgb = [torch.from_numpy(f[0]).cuda(dev) for f in frames]
+    d_dep = [torch.from_numpy(f[1]).cuda(dev) for f in frames]
+    h_rgb = [torch.from_numpy(f[0]).pin_memory() for f in frames]
+    h_dep = [torch.from_numpy(f[1]).pin_memory() for f in frames]
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        tns = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    def timed(run_step, steps, warmup):
+        eng = SupersurfelFusion(dev).initialize(CamParam(*cam), **PARAMS)
+        for s in range(warmup):
+            run_step(eng, s)
+        barrier()
+        l0 = eng.launchCount()
+        eng.timerStart()                      # CUDA event on the engine's stream
+        w0 = time.perf_counter()
+        for s in range(warmup, warmup + steps):
+            run_step(eng, s)
+        ms = eng.timerStop()                  # records + synchronises
+        wall = (time.perf_counter() - w0) * 1e3
+        barrier()
+        launches = eng.launchCount() - l0
+        stats = eng.getFrameStats()
+        eng.close()
+        return max_over_ranks(ms), max_over_ranks(wall), launches, stats
+
+    def step_resident(eng, s):
+        k = frame_index(s)
+        eng.processFrameDevice(d_rgb[k], d_dep[k])
+
+    def step_e2e(eng, s):
+        k = frame_index(s)
+        eng.processFrame(h_rgb[k], h_dep[k])
+
+    sampler = ClockSampler(dev)
+    sampler.start()
+    ms, wall_ms, launches, stats = timed(step_resident, args.steps, args.warmup)
+    ms_e, wall_e, _, _ = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roof = icp_roofline(dev, peaks) if world == 1 else None
+    cpu = None
+    if world == 1:
+        fps_cpu, dt = time_cpu_oracle(frames, cam, 60)
+        cpu = {"value": fps_cpu, "unit": "frames/s", "cores": 1, "kind": "port",
+               "sample": "60 frames of the workload sequence (%.1f s of CPU work), CPU oracle restatement, 1 thread" % dt}
+    total_frames = args.steps * world
+    value = total_frames / (ms * 1e-3)
+    e2e = total_frames / (ms_e * 1e-3)
+    line = {
+        "metric": "RGB-D frames/sec @640x480", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD if world == 1 else "configs[3]: %d independent 640x480 synthetic sequences, one per GPU, no NCCL on the data path" % world,
+                   "params": "launch/supersurfel_fusion_rgbd_benchmark.launch", "frames_per_gpu": args.steps,
+                   "l2_policy": "per-frame working set (~9 MB images + model) is L2 resident by nature of the workload; "
+                                "the roofline kernel streams 604 MB per launch (> 126 MB L2), no flush needed",
+                   "timing": "CUDA events on the engine stream, max over ranks"},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": 640 * 480 * 7, "d2h_bytes_per_step": 104,
+                "ms_per_step": ms_e / args.steps, "wall_ms_per_step": wall_e / args.steps},
+        "wall_ms_per_step": wall_ms / args.steps,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "last_frame_stats": stats,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,217 @@
+/* libssf -- C-ABI of the B200-native supersurfel tracking-and-fusion hot path.
+ *
+ * Drop-in boundary for the reference's C++ class supersurfel_fusion::SupersurfelFusion
+ * (reference: core/include/supersurfel_fusion/supersurfel_fusion.hpp:40-143).  Every
+ * entry point cites the reference interface it replaces.  Plain C types only: no
+ * torch, thrust, OpenCV or Eigen types cross this boundary.
+ *
+ * Conventions
+ *  - every function returns an int status: SSF_OK (0) or a negative SSF_ERR_* code;
+ *    the reference instead prints and exit(-1)s (cuda_error_check.h:30-66).
+ *    ssf_last_error() returns a human-readable message for the last failure.
+ *  - a handle is bound to one CUDA device and one stream and is NOT thread-safe
+ *    (the reference is driven from a single ROS callback thread,
+ *    node/supersurfel_fusion_node.cpp:74-85).  N handles on N devices from N host
+ *    threads / processes is the supported multi-GPU mode.
+ *  - "host-or-device pointer": the argument may point to pageable/pinned host
+ *    memory or to device memory of the handle's device (copies use
+ *    cudaMemcpyDefault).
+ *  - supersurfel arrays use the member layout of the reference's Supersurfels
+ *    container (core/include/supersurfel_fusion/supersurfels.hpp:32-41):
+ *      positions float[N][3], colors float[N][3] (RGB 0..255), stamps int[N][2],
+ *      orientations float[N][9] (rows e1,e2,normal), shapes float[N][6]
+ *      (xx,xy,xz,yy,yz,zz), dims float[N][2], confidences float[N].
+ *  - poses are (R row-major 3x3, t) mapping camera to world, as Transform3
+ *    (core/include/supersurfel_fusion/matrix_types.h:38-42).
+ */
+#ifndef SSF_H
+#define SSF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSF_OK 0
+#define SSF_ERR_INVALID_ARG (-1)
+#define SSF_ERR_CUDA (-2)
+#define SSF_ERR_NO_DEVICE (-3)
+#define SSF_ERR_IO (-4)
+#define SSF_ERR_STATE (-5)
+
+typedef struct SsfEngine* SsfHandle;
+
+/* core/include/supersurfel_fusion/cam_param.hpp:27-31 */
+typedef struct SsfCamParam {
+  float fx, fy, cx, cy;
+  int height, width;
+} SsfCamParam;
+
+/* The hot-path arguments of SupersurfelFusion::initialize
+ * (supersurfel_fusion.hpp:46-74), same names, same defaults.  The sparse-VO
+ * arguments (nb_features ... untracked_threshold) belong to an out-of-scope
+ * neighbour and are not part of this struct; enable_loop_closure / enable_mod are
+ * accepted for signature compatibility and must be 0. */
+typedef struct SsfConfig {
+  SsfCamParam cam;
+  int cell_size;          /* 16 */
+  float lambda_pos;       /* 50 */
+  float lambda_bound;     /* 1000 */
+  float lambda_size;      /* 10000 */
+  float lambda_disp;      /* 1e6 */
+  float thresh_disp;      /* 1e-4 */
+  int seg_iter;           /* 10 */
+  int seg_use_ransac;     /* 1 */
+  int nb_samples;         /* 16 */
+  int filter_iter;        /* 4 */
+  float filter_alpha;     /* 0.1 */
+  float filter_beta;      /* 1.0 */
+  float filter_threshold; /* 0.05 */
+  float range_min;        /* 0.2 */
+  float range_max;        /* 5.0 */
+  int delta_t;            /* 20 */
+  float conf_thresh;      /* 2500 */
+  int nb_supersurfels_max;/* 50000 */
+  int icp_iter;           /* 10 */
+  double icp_cov_thresh;  /* 0.04 */
+  int enable_loop_closure;/* must be 0 */
+  int enable_mod;         /* must be 0 */
+} SsfConfig;
+
+/* Host-or-device view of supersurfel arrays (any member may be NULL = skip). */
+typedef struct SsfSurfels {
+  float* positions;
+  float* colors;
+  int32_t* stamps;
+  float* orientations;
+  float* shapes;
+  float* dims;
+  float* confidences;
+} SsfSurfels;
+
+/* What the reference prints per frame (supersurfel_fusion.cu:516-528,
+ * dense_registration.cu:336-341) returned as data. */
+typedef struct SsfFrameStats {
+  int32_t stamp;            /* stamp of the processed frame */
+  int32_t nb_supersurfels;  /* model size after the update */
+  int32_t nb_visible;       /* active (in-view) prefix length */
+  int32_t nb_removed;
+  int32_t nb_matched;       /* frame superpixels fused into the model */
+  int32_t nb_inserted;
+  int32_t icp_ran;          /* 0 on the bootstrap frame */
+  int32_t icp_valid;
+  int32_t icp_iters;
+  float icp_inliers;
+  double icp_error;         /* sqrt(r / inliers) of the last built system */
+  float gpu_ms;             /* device time of the frame (CUDA events) */
+} SsfFrameStats;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+/* Defaults of initialize() (supersurfel_fusion.hpp:46-74); camera = TUM fr1. */
+int ssf_config_default(SsfConfig* cfg);
+/* SupersurfelFusion() + initialize() (supersurfel_fusion.cu:49-164). */
+int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out);
+/* ~SupersurfelFusion() (supersurfel_fusion.cu:40-47). */
+int ssf_destroy(SsfHandle h);
+/* Run all work of this handle on an existing CUDA stream (cudaStream_t / CUstream
+ * passed as void*); NULL restores the handle's own stream. */
+int ssf_set_stream(SsfHandle h, void* cuda_stream);
+const char* ssf_last_error(SsfHandle h);
+/* isInitialized() (supersurfel_fusion.hpp:85) */
+int ssf_is_initialized(SsfHandle h);
+
+/* ---- the per-frame entry point ------------------------------------------- */
+/* processFrame(rgb_h 8UC3 RGB, depth_h 32FC1 metres) (supersurfel_fusion.cu:166-530).
+ * rgb/depth: host-or-device pointers, strides in BYTES (cv::Mat::step).
+ * pose_prior_Rt12: optional camera pose prior (R row-major 9 floats, then t), the
+ * stand-in for the sparse-VO pose (supersurfel_fusion.cu:225-228); NULL keeps the
+ * previous fused pose.  Depth is expected already bilateral-filtered unless
+ * SSF_FLAG_BILATERAL is set.  Synchronous, like the reference. */
+#define SSF_FLAG_BILATERAL 1u
+int ssf_process_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth,
+                      size_t depth_stride, const float* pose_prior_Rt12, uint32_t flags);
+/* Same, inputs already resident on the handle's device (dense, stride = width). */
+int ssf_process_frame_device(SsfHandle h, const uint8_t* rgb_dev, const float* depth_dev,
+                             const float* pose_prior_Rt12, uint32_t flags);
+int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out);
+
+/* ---- getters (supersurfel_fusion.hpp:85-91) ------------------------------ */
+int ssf_get_pose(SsfHandle h, float R[9], float t[3]);          /* getPose() */
+int ssf_set_pose(SsfHandle h, const float R[9], const float t[3]); /* loop-closure / relocalisation hook */
+int ssf_get_stamp(SsfHandle h, int* stamp);                      /* getStamp() */
+int ssf_set_stamp(SsfHandle h, int stamp);
+int ssf_get_counts(SsfHandle h, int* nb_supersurfels, int* nb_visible, int* nb_removed); /* getnbSupersurfels() */
+int ssf_get_nb_superpixels(SsfHandle h, int* nb_superpixels);
+/* getModel() / getFrame(): copy the first n rows into caller buffers
+ * (host-or-device); the node does the same through thrust::host_vector
+ * (node/supersurfel_fusion_node.cpp:306-310). */
+int ssf_copy_model(SsfHandle h, const SsfSurfels* dst, int n);
+int ssf_copy_frame(SsfHandle h, const SsfSurfels* dst);
+/* tps->getIndexImage() / getBoundaryImage() / getInliersImage() / getDispImage()
+ * (TPS_RGBD.hpp:77-81), the slanted-plane depth (computeDepthImage, TPS_RGBD.cu:507-525)
+ * and tps->getSuperpixels() as S x 12 floats (TPS_RGBD.hpp:33-38).  NULL = skip. */
+int ssf_get_segmentation(SsfHandle h, int32_t* labels, int32_t* bound, uint8_t* inliers, float* disp,
+                         float* slanted_depth, float* superpixels, uint8_t* rgba);
+/* computeSuperpixelSegIm (supersurfel_fusion.cu:635-640): H x W x 3 preview, boundaries white. */
+int ssf_render_preview(SsfHandle h, uint8_t* bgr);
+/* computeSlantedPlaneIm (supersurfel_fusion.cu:642-650): slanted depth, float H x W. */
+int ssf_get_slanted_depth(SsfHandle h, float* depth);
+/* exportModel(filename) (supersurfel_fusion.cu:595-633), same text format. */
+int ssf_export_model(SsfHandle h, const char* path);
+/* extractLocalPointCloud (supersurfel_fusion.cu:884-927): stable supersurfels within
+ * `radius` of the camera, in camera coordinates.  capacity rows available in the
+ * caller buffers (host-or-device); *count receives the number written. */
+int ssf_extract_local_point_cloud(SsfHandle h, float radius, float* positions, float* normals,
+                                  int capacity, int* count);
+/* MOD hook: mask[S] != 0 marks a frame supersurfel dynamic => confidence = -1
+ * (what motion_detection.cu:573 does to frame.confidences). */
+int ssf_invalidate_frame_supersurfels(SsfHandle h, const uint8_t* mask);
+/* Loop-closure hook: rigidly move the whole model (applyTransformSuperSurfel,
+ * supersurfel_fusion_kernels.cu:469-488). */
+int ssf_transform_model(SsfHandle h, const float R[9], const float t[3]);
+
+/* ---- stage entry points (for parity tests and callers that drive stages) --- */
+/* State injection: host-or-device arrays in the layouts above. */
+int ssf_set_model(SsfHandle h, const SsfSurfels* src, int nb_supersurfels, int nb_visible);
+int ssf_set_frame(SsfHandle h, const SsfSurfels* src);
+int ssf_set_segmentation(SsfHandle h, const int32_t* labels, const int32_t* bound, const uint8_t* inliers,
+                         const float* slanted_depth, const uint8_t* rgba);
+/* tps->compute + filter + computeDepthImage (supersurfel_fusion.cu:189-191). */
+int ssf_tps_segment(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth,
+                    size_t depth_stride);
+/* RANSAC candidate planes of the last ssf_tps_segment: S x nb_samples x 4 floats. */
+int ssf_get_ransac_samples(SsfHandle h, float* samples);
+/* generateSupersurfels() (supersurfel_fusion.cu:551-593). */
+int ssf_generate_supersurfels(SsfHandle h);
+/* One launch of the symmetric ICP system build at the view transform (R,t)
+ * (computeSymmetricICPSystem<128>, dense_registration_kernels.cuh:175-291):
+ * out29 = JtJ[21] (upper triangle, row-major), Jtr[6], r, inliers
+ * (MotionTrackingData, dense_registration_types.hpp:55-60).  n_src <= 0 uses the
+ * model's visible prefix. */
+int ssf_icp_system(SsfHandle h, const float R[9], const float t[3], int n_src, float out29[29]);
+/* Enqueue-only variant for timing: `launches` back-to-back builds on the handle's
+ * stream, no host sync, result left on the device. */
+int ssf_icp_system_enqueue(SsfHandle h, const float R[9], const float t[3], int n_src, int launches);
+/* featureConstrainedSymmetricICP (dense_registration.cu:245-424), whole
+ * Gauss-Newton loop on the device.  R_init/t_init = view transform (inverse of the
+ * prior pose); NULL = derive from the handle's current pose.  Does not modify the
+ * pose.  Returns R_rel/t_rel (identity/zero when invalid). */
+int ssf_icp(SsfHandle h, const float* R_init, const float* t_init, float out29[29], float R_rel[9],
+            float t_rel[3], int* iters, int* valid);
+/* Model update block of processFrame (supersurfel_fusion.cu:351-483) at the
+ * handle's current pose and stamp. */
+int ssf_fuse(SsfHandle h);
+
+/* ---- timing helpers (CUDA events on the handle's stream) ------------------ */
+int ssf_timer_start(SsfHandle h);
+int ssf_timer_stop(SsfHandle h, float* ms); /* records, synchronises, returns elapsed */
+int ssf_synchronize(SsfHandle h);
+/* Number of kernels this library launched on the handle since creation. */
+int ssf_get_launch_count(SsfHandle h, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSF_H */

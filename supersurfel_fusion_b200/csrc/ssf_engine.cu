@@ -1,0 +1,717 @@
+// libssf C-ABI (include/ssf.h): engine lifetime, the per-frame sequence and the stage
+// entry points.  Host logic mirrors SupersurfelFusion::initialize / processFrame
+// (reference: core/src/supersurfel_fusion.cu:49-164, 166-530) with the whole frame
+// enqueued on one stream and replayed as a CUDA graph: no per-frame allocation, no
+// intermediate device synchronisation, one small read-back at the end of the frame.
+#include "ssf_engine.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+namespace ssf {
+
+void launch_icp_set_transform(Engine* e, const float* R, const float* t);
+size_t tps_rng_state_bytes();
+
+struct FrameReport {
+  Counters counters;
+  DevicePose pose;
+  int icp_active, icp_valid, icp_iters;
+  float icp_inliers;
+  double icp_error;
+};
+
+__global__ void frame_end_kernel(Counters* counters, const DevicePose* pose, const IcpState* icp, FrameReport* rep,
+                                 int advance) {
+  rep->counters = *counters;
+  rep->pose = *pose;
+  rep->icp_active = icp->active;
+  rep->icp_valid = icp->active ? icp->valid : 0;
+  rep->icp_iters = icp->active ? icp->iter : 0;
+  rep->icp_inliers = icp->active ? icp->inliers : 0.0f;
+  rep->icp_error = icp->active ? icp->error : 0.0;
+  if (advance) counters->stamp += 1;   // supersurfel_fusion.cu:521
+}
+
+__global__ void split_lmap_kernel(const int2* lmap, float* slanted, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) slanted[i] = __int_as_float(lmap[i].y);
+}
+
+struct EngineImpl : public SsfEngine {
+  uint64_t launches_per_frame;
+  FrameReport* d_report;
+  FrameReport* h_report;
+  float* h_prior;          // pinned 12 floats
+  cudaGraphExec_t graph_exec;
+  bool graph_ready;
+  bool use_graph;
+  bool created;
+};
+
+static inline int round4(int n) { return (n + 3) & ~3; }
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) {
+  cudaError_t err = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+  if (err == cudaSuccess) err = cudaMemset(*p, 0, count * sizeof(T));
+  return err;
+}
+
+static void enqueue_frame(EngineImpl* e) {
+  launch_ingest(e, e->in_rgb, (size_t)e->W * 3, e->in_depth, (size_t)e->W * 4);
+  launch_tps(e);
+  launch_extract(e);
+  launch_icp_begin_from_pose(e);
+  launch_icp_loop(e);
+  launch_icp_finish(e, true);
+  launch_fuse(e);
+  frame_end_kernel<<<1, 1, 0, e->stream>>>(e->counters, e->pose, e->icp, e->d_report, 1);
+  e->launches++;
+}
+
+static int ensure_scratch(EngineImpl* e, size_t bytes) {
+  if (e->scratch_bytes >= bytes) return SSF_OK;
+  if (e->scratch) cudaFree(e->scratch);
+  e->scratch = nullptr;
+  e->scratch_bytes = 0;
+  SSF_CUDA(e, cudaMalloc(&e->scratch, bytes));
+  e->scratch_bytes = bytes;
+  return SSF_OK;
+}
+
+// member-layout view carved out of the scratch buffer
+static SsfSurfels scratch_view(void* base, int n) {
+  char* p = reinterpret_cast<char*>(base);
+  SsfSurfels v;
+  v.positions = reinterpret_cast<float*>(p); p += (size_t)n * 12;
+  v.colors = reinterpret_cast<float*>(p); p += (size_t)n * 12;
+  v.stamps = reinterpret_cast<int32_t*>(p); p += (size_t)n * 8;
+  v.orientations = reinterpret_cast<float*>(p); p += (size_t)n * 36;
+  v.shapes = reinterpret_cast<float*>(p); p += (size_t)n * 24;
+  v.dims = reinterpret_cast<float*>(p); p += (size_t)n * 8;
+  v.confidences = reinterpret_cast<float*>(p);
+  return v;
+}
+
+static int copy_members(EngineImpl* e, const SsfSurfels& dst, const SsfSurfels& src, int n) {
+  if (dst.positions) SSF_CUDA(e, cudaMemcpyAsync(dst.positions, src.positions, (size_t)n * 12, cudaMemcpyDefault, e->stream));
+  if (dst.colors) SSF_CUDA(e, cudaMemcpyAsync(dst.colors, src.colors, (size_t)n * 12, cudaMemcpyDefault, e->stream));
+  if (dst.stamps) SSF_CUDA(e, cudaMemcpyAsync(dst.stamps, src.stamps, (size_t)n * 8, cudaMemcpyDefault, e->stream));
+  if (dst.orientations) SSF_CUDA(e, cudaMemcpyAsync(dst.orientations, src.orientations, (size_t)n * 36, cudaMemcpyDefault, e->stream));
+  if (dst.shapes) SSF_CUDA(e, cudaMemcpyAsync(dst.shapes, src.shapes, (size_t)n * 24, cudaMemcpyDefault, e->stream));
+  if (dst.dims) SSF_CUDA(e, cudaMemcpyAsync(dst.dims, src.dims, (size_t)n * 8, cudaMemcpyDefault, e->stream));
+  if (dst.confidences) SSF_CUDA(e, cudaMemcpyAsync(dst.confidences, src.confidences, (size_t)n * 4, cudaMemcpyDefault, e->stream));
+  return SSF_OK;
+}
+
+static int read_report(EngineImpl* e, bool advance) {
+  frame_end_kernel<<<1, 1, 0, e->stream>>>(e->counters, e->pose, e->icp, e->d_report, advance ? 1 : 0);
+  e->launches++;
+  SSF_CUDA(e, cudaMemcpyAsync(e->h_report, e->d_report, sizeof(FrameReport), cudaMemcpyDeviceToHost, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+static void fill_stats(EngineImpl* e, float gpu_ms) {
+  const FrameReport& r = *e->h_report;
+  SsfFrameStats& s = e->stats;
+  s.stamp = r.counters.stamp;
+  s.nb_supersurfels = r.counters.nb_supersurfels;
+  s.nb_visible = r.counters.nb_visible;
+  s.nb_removed = r.counters.nb_removed;
+  s.nb_matched = r.counters.nb_matched;
+  s.nb_inserted = r.counters.nb_inserted;
+  s.icp_ran = r.icp_active;
+  s.icp_valid = r.icp_valid;
+  s.icp_iters = r.icp_iters;
+  s.icp_inliers = r.icp_inliers;
+  s.icp_error = r.icp_error;
+  s.gpu_ms = gpu_ms;
+}
+
+}  // namespace ssf
+
+using namespace ssf;
+
+#define H_CHECK(h)                                  \
+  if (!(h)) return SSF_ERR_INVALID_ARG;             \
+  EngineImpl* e = static_cast<EngineImpl*>(h);      \
+  cudaSetDevice(e->device)
+
+extern "C" {
+
+int ssf_config_default(SsfConfig* c) {
+  if (!c) return SSF_ERR_INVALID_ARG;
+  memset(c, 0, sizeof(*c));
+  c->cam.fx = 525.0f; c->cam.fy = 525.0f; c->cam.cx = 319.5f; c->cam.cy = 239.5f;
+  c->cam.height = 480; c->cam.width = 640;
+  c->cell_size = 16;
+  c->lambda_pos = 50.0f; c->lambda_bound = 1000.0f; c->lambda_size = 10000.0f; c->lambda_disp = 1000000.0f;
+  c->thresh_disp = 0.0001f;
+  c->seg_iter = 10; c->seg_use_ransac = 1; c->nb_samples = 16;
+  c->filter_iter = 4; c->filter_alpha = 0.1f; c->filter_beta = 1.0f; c->filter_threshold = 0.05f;
+  c->range_min = 0.2f; c->range_max = 5.0f;
+  c->delta_t = 20; c->conf_thresh = 2500.0f; c->nb_supersurfels_max = 50000;
+  c->icp_iter = 10; c->icp_cov_thresh = 0.04;
+  c->enable_loop_closure = 0; c->enable_mod = 0;
+  return SSF_OK;
+}
+
+int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
+  if (!cfg || !out) return SSF_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (cfg->cam.width <= 0 || cfg->cam.height <= 0 || cfg->cell_size < 2 || cfg->nb_supersurfels_max <= 0 ||
+      cfg->nb_samples <= 0 || cfg->nb_samples > 1024 || cfg->seg_iter < 0 || cfg->icp_iter < 1 ||
+      cfg->enable_loop_closure || cfg->enable_mod)
+    return SSF_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return SSF_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return SSF_ERR_NO_DEVICE;
+  EngineImpl* e = new (std::nothrow) EngineImpl();
+  if (!e) return SSF_ERR_INVALID_ARG;
+  e->cfg = *cfg;
+  e->device = device;
+  e->launches = 0;
+  e->graph_ready = false;
+  e->use_graph = true;
+  e->created = false;
+  e->W = cfg->cam.width; e->H = cfg->cam.height;
+  e->npix = (size_t)e->W * e->H;
+  e->gx = (e->W + cfg->cell_size - 1) / cfg->cell_size;
+  e->gy = (e->H + cfg->cell_size - 1) / cfg->cell_size;
+  e->S = e->gx * e->gy;
+  e->cap = cfg->nb_supersurfels_max > e->S ? cfg->nb_supersurfels_max : e->S;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  const int sms = prop.multiProcessorCount;
+  const int need_blocks = (e->cap + 1023) / 1024;
+  e->icp_grid = need_blocks < 2 * sms ? need_blocks : 2 * sms;
+
+  cudaError_t err = cudaSuccess;
+#define A(call) if (err == cudaSuccess) err = (call)
+  A(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  e->stream = e->own_stream;
+  A(cudaEventCreate(&e->ev0)); A(cudaEventCreate(&e->ev1)); A(cudaEventCreate(&e->evf0)); A(cudaEventCreate(&e->evf1));
+  const size_t N = e->npix;
+  const int S = e->S, nbs = cfg->nb_samples;
+  A(dalloc(&e->rgba, N)); A(dalloc(&e->disp, N)); A(dalloc(&e->labels, N)); A(dalloc(&e->bound, N));
+  A(dalloc(&e->inliers, N)); A(dalloc(&e->lmap, N)); A(dalloc(&e->in_rgb, N * 3)); A(dalloc(&e->in_depth, N));
+  A(dalloc(&e->sp, (size_t)S)); A(dalloc(&e->sums, (size_t)S));
+  {
+    char* p = nullptr;
+    A(dalloc(&p, (size_t)S * nbs * (sizeof(float4) + sizeof(int))));
+    e->samples = reinterpret_cast<float4*>(p);
+    char* r = nullptr;
+    A(dalloc(&r, (size_t)S * nbs * tps_rng_state_bytes()));
+    e->rng = r;
+  }
+  A(dalloc(&e->filt_a, (size_t)S * 8)); A(dalloc(&e->filt_b, (size_t)S * 8));
+  A(dalloc(&e->xsums, (size_t)S * 16));
+  e->frame.stride = round4(S);
+  e->model.stride = e->model_alt.stride = round4(e->cap);
+  A(dalloc(&e->frame.base, (size_t)P_COUNT * e->frame.stride));
+  A(dalloc(&e->model.base, (size_t)P_COUNT * e->model.stride));
+  A(dalloc(&e->model_alt.base, (size_t)P_COUNT * e->model_alt.stride));
+  A(dalloc(&e->ftab, (size_t)2 * S)); A(dalloc(&e->matched, (size_t)S)); A(dalloc(&e->best, (size_t)S));
+  A(dalloc(&e->states, (size_t)e->cap));
+  A(dalloc(&e->scan_tmp, (size_t)8 + 4 * ((size_t)(e->cap + 1023) / 1024)));
+  A(dalloc(&e->icp, (size_t)1)); A(dalloc(&e->icp_partials, (size_t)e->icp_grid * 32));
+  A(dalloc(&e->counters, (size_t)1)); A(dalloc(&e->pose, (size_t)1));
+  A(dalloc(&e->d_report, (size_t)1));
+  A(cudaMallocHost(reinterpret_cast<void**>(&e->h_report), sizeof(FrameReport)));
+  A(cudaMallocHost(reinterpret_cast<void**>(&e->h_prior), 12 * sizeof(float)));
+#undef A
+  if (err != cudaSuccess) {
+    fprintf(stderr, "ssf_create: %s\n", cudaGetErrorString(err));
+    ssf_destroy(e);
+    return SSF_ERR_CUDA;
+  }
+  // identity pose (supersurfel_fusion.cu:133-136)
+  DevicePose ident = {{1, 0, 0, 0, 1, 0, 0, 0, 1}, {0, 0, 0}};
+  cudaMemcpy(e->pose, &ident, sizeof(ident), cudaMemcpyHostToDevice);
+  memset(e->h_report, 0, sizeof(FrameReport));
+  e->h_report->pose = ident;
+  tps_init_rng(e);   // initRandStates_kernel, once (TPS_RGBD.cu:123)
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess) { ssf_destroy(e); return SSF_ERR_CUDA; }
+  e->created = true;
+  *out = e;
+  return SSF_OK;
+}
+
+int ssf_destroy(SsfHandle h) {
+  if (!h) return SSF_ERR_INVALID_ARG;
+  EngineImpl* e = static_cast<EngineImpl*>(h);
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  if (e->graph_ready) cudaGraphExecDestroy(e->graph_exec);
+  void* bufs[] = {e->rgba, e->disp, e->labels, e->bound, e->inliers, e->lmap, e->in_rgb, e->in_depth, e->sp, e->sums,
+                  e->samples, e->rng, e->filt_a, e->filt_b, e->xsums, e->frame.base, e->model.base,
+                  e->model_alt.base, e->ftab, e->matched, e->best, e->states, e->scan_tmp, e->icp, e->icp_partials,
+                  e->counters, e->pose, e->d_report, e->scratch};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  if (e->h_report) cudaFreeHost(e->h_report);
+  if (e->h_prior) cudaFreeHost(e->h_prior);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->evf0) cudaEventDestroy(e->evf0);
+  if (e->evf1) cudaEventDestroy(e->evf1);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+  return SSF_OK;
+}
+
+int ssf_set_stream(SsfHandle h, void* cuda_stream) {
+  H_CHECK(h);
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+  if (e->graph_ready) { cudaGraphExecDestroy(e->graph_exec); e->graph_ready = false; }
+  return SSF_OK;
+}
+
+const char* ssf_last_error(SsfHandle h) {
+  if (!h) return "invalid handle";
+  return static_cast<EngineImpl*>(h)->err.c_str();
+}
+
+int ssf_is_initialized(SsfHandle h) { return (h && static_cast<EngineImpl*>(h)->created) ? 1 : 0; }
+
+static int run_frame(EngineImpl* e, const float* prior, uint32_t flags) {
+  if (flags & SSF_FLAG_BILATERAL) { e->err = "SSF_FLAG_BILATERAL: ingest filter not built yet"; return SSF_ERR_INVALID_ARG; }
+  if (prior) {
+    memcpy(e->h_prior, prior, 12 * sizeof(float));
+    SSF_CUDA(e, cudaMemcpyAsync(e->pose, e->h_prior, 12 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  }
+  SSF_CUDA(e, cudaEventRecord(e->evf0, e->stream));
+  if (e->use_graph) {
+    if (!e->graph_ready) {
+      cudaGraph_t g;
+      const uint64_t before = e->launches;
+      SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+      enqueue_frame(e);
+      SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
+      e->launches_per_frame = e->launches - before;
+      e->launches = before;
+      SSF_CUDA(e, cudaGraphInstantiate(&e->graph_exec, g, 0));
+      cudaGraphDestroy(g);
+      e->graph_ready = true;
+    }
+    SSF_CUDA(e, cudaGraphLaunch(e->graph_exec, e->stream));
+    e->launches += e->launches_per_frame;
+  } else {
+    enqueue_frame(e);
+  }
+  SSF_CUDA(e, cudaEventRecord(e->evf1, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(e->h_report, e->d_report, sizeof(FrameReport), cudaMemcpyDeviceToHost, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_CUDA(e, cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e->evf0, e->evf1);
+  fill_stats(e, ms);
+  return SSF_OK;
+}
+
+int ssf_process_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth, size_t depth_stride,
+                      const float* pose_prior_Rt12, uint32_t flags) {
+  H_CHECK(h);
+  if (!rgb || !depth) return SSF_ERR_INVALID_ARG;
+  if (rgb_stride == 0) rgb_stride = (size_t)e->W * 3;
+  if (depth_stride == 0) depth_stride = (size_t)e->W * 4;
+  if (rgb_stride < (size_t)e->W * 3 || depth_stride < (size_t)e->W * 4) return SSF_ERR_INVALID_ARG;
+  // rgb.upload / depth.upload (supersurfel_fusion.cu:173-174)
+  SSF_CUDA(e, cudaMemcpy2DAsync(e->in_rgb, (size_t)e->W * 3, rgb, rgb_stride, (size_t)e->W * 3, e->H, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpy2DAsync(e->in_depth, (size_t)e->W * 4, depth, depth_stride, (size_t)e->W * 4, e->H, cudaMemcpyDefault, e->stream));
+  return run_frame(e, pose_prior_Rt12, flags);
+}
+
+int ssf_process_frame_device(SsfHandle h, const uint8_t* rgb_dev, const float* depth_dev, const float* pose_prior_Rt12,
+                             uint32_t flags) {
+  H_CHECK(h);
+  if (!rgb_dev || !depth_dev) return SSF_ERR_INVALID_ARG;
+  SSF_CUDA(e, cudaMemcpyAsync(e->in_rgb, rgb_dev, e->npix * 3, cudaMemcpyDeviceToDevice, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(e->in_depth, depth_dev, e->npix * 4, cudaMemcpyDeviceToDevice, e->stream));
+  return run_frame(e, pose_prior_Rt12, flags);
+}
+
+int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out) {
+  H_CHECK(h);
+  if (!out) return SSF_ERR_INVALID_ARG;
+  *out = e->stats;
+  return SSF_OK;
+}
+
+int ssf_get_pose(SsfHandle h, float R[9], float t[3]) {
+  H_CHECK(h);
+  int rc = read_report(e, false);
+  if (rc) return rc;
+  memcpy(R, e->h_report->pose.R, 36);
+  memcpy(t, e->h_report->pose.t, 12);
+  return SSF_OK;
+}
+
+int ssf_set_pose(SsfHandle h, const float R[9], const float t[3]) {
+  H_CHECK(h);
+  memcpy(e->h_prior, R, 36);
+  memcpy(e->h_prior + 9, t, 12);
+  SSF_CUDA(e, cudaMemcpyAsync(e->pose, e->h_prior, 48, cudaMemcpyHostToDevice, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_get_stamp(SsfHandle h, int* stamp) {
+  H_CHECK(h);
+  int rc = read_report(e, false);
+  if (rc) return rc;
+  *stamp = e->h_report->counters.stamp;
+  return SSF_OK;
+}
+
+int ssf_set_stamp(SsfHandle h, int stamp) {
+  H_CHECK(h);
+  SSF_CUDA(e, cudaMemcpyAsync(&e->counters->stamp, &stamp, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_get_counts(SsfHandle h, int* nb_supersurfels, int* nb_visible, int* nb_removed) {
+  H_CHECK(h);
+  int rc = read_report(e, false);
+  if (rc) return rc;
+  if (nb_supersurfels) *nb_supersurfels = e->h_report->counters.nb_supersurfels;
+  if (nb_visible) *nb_visible = e->h_report->counters.nb_visible;
+  if (nb_removed) *nb_removed = e->h_report->counters.nb_removed;
+  return SSF_OK;
+}
+
+int ssf_get_nb_superpixels(SsfHandle h, int* n) {
+  H_CHECK(h);
+  *n = e->S;
+  return SSF_OK;
+}
+
+static int copy_set_out(EngineImpl* e, const SurfelSet& set, const SsfSurfels* dst, int n) {
+  if (!dst || n < 0) return SSF_ERR_INVALID_ARG;
+  if (n == 0) return SSF_OK;
+  int rc = ensure_scratch(e, (size_t)n * 104);
+  if (rc) return rc;
+  SsfSurfels sv = scratch_view(e->scratch, n);
+  launch_pack(e, set, n, sv);
+  rc = copy_members(e, *dst, sv, n);
+  if (rc) return rc;
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+static int copy_set_in(EngineImpl* e, const SsfSurfels* src, int n, const SurfelSet& set) {
+  if (!src || n < 0) return SSF_ERR_INVALID_ARG;
+  if (n == 0) return SSF_OK;
+  int rc = ensure_scratch(e, (size_t)n * 104);
+  if (rc) return rc;
+  SsfSurfels sv = scratch_view(e->scratch, n);
+  SsfSurfels present = sv;
+  if (!src->positions) present.positions = nullptr;
+  if (!src->colors) present.colors = nullptr;
+  if (!src->stamps) present.stamps = nullptr;
+  if (!src->orientations) present.orientations = nullptr;
+  if (!src->shapes) present.shapes = nullptr;
+  if (!src->dims) present.dims = nullptr;
+  if (!src->confidences) present.confidences = nullptr;
+  rc = copy_members(e, present, *src, n);
+  if (rc) return rc;
+  launch_unpack(e, present, n, set);
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_copy_model(SsfHandle h, const SsfSurfels* dst, int n) {
+  H_CHECK(h);
+  if (n > e->cap) return SSF_ERR_INVALID_ARG;
+  return copy_set_out(e, e->model, dst, n);
+}
+
+int ssf_copy_frame(SsfHandle h, const SsfSurfels* dst) {
+  H_CHECK(h);
+  return copy_set_out(e, e->frame, dst, e->S);
+}
+
+int ssf_get_segmentation(SsfHandle h, int32_t* labels, int32_t* bound, uint8_t* inliers, float* disp,
+                         float* slanted_depth, float* superpixels, uint8_t* rgba) {
+  H_CHECK(h);
+  const size_t N = e->npix;
+  if (labels) SSF_CUDA(e, cudaMemcpyAsync(labels, e->labels, N * 4, cudaMemcpyDefault, e->stream));
+  if (bound) SSF_CUDA(e, cudaMemcpyAsync(bound, e->bound, N * 4, cudaMemcpyDefault, e->stream));
+  if (inliers) SSF_CUDA(e, cudaMemcpyAsync(inliers, e->inliers, N, cudaMemcpyDefault, e->stream));
+  if (disp) SSF_CUDA(e, cudaMemcpyAsync(disp, e->disp, N * 4, cudaMemcpyDefault, e->stream));
+  if (rgba) SSF_CUDA(e, cudaMemcpyAsync(rgba, e->rgba, N * 4, cudaMemcpyDefault, e->stream));
+  if (superpixels) SSF_CUDA(e, cudaMemcpyAsync(superpixels, e->sp, (size_t)e->S * sizeof(Superpixel), cudaMemcpyDefault, e->stream));
+  if (slanted_depth) {
+    int rc = ensure_scratch(e, N * 4);
+    if (rc) return rc;
+    split_lmap_kernel<<<(unsigned)((N + 255) / 256), 256, 0, e->stream>>>(e->lmap, reinterpret_cast<float*>(e->scratch), N);
+    e->launches++;
+    SSF_CUDA(e, cudaMemcpyAsync(slanted_depth, e->scratch, N * 4, cudaMemcpyDefault, e->stream));
+  }
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_get_slanted_depth(SsfHandle h, float* depth) {
+  return ssf_get_segmentation(h, nullptr, nullptr, nullptr, nullptr, depth, nullptr, nullptr);
+}
+
+int ssf_render_preview(SsfHandle h, uint8_t* bgr) {
+  H_CHECK(h);
+  if (!bgr) return SSF_ERR_INVALID_ARG;
+  int rc = ensure_scratch(e, e->npix * 3);
+  if (rc) return rc;
+  launch_preview(e, reinterpret_cast<uint8_t*>(e->scratch));
+  SSF_CUDA(e, cudaMemcpyAsync(bgr, e->scratch, e->npix * 3, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_export_model(SsfHandle h, const char* path) {
+  H_CHECK(h);
+  if (!path) return SSF_ERR_INVALID_ARG;
+  int rc = read_report(e, false);
+  if (rc) return rc;
+  const int n = e->h_report->counters.nb_supersurfels;
+  std::vector<float> pos((size_t)n * 3), col((size_t)n * 3), ori((size_t)n * 9), shp((size_t)n * 6), dms((size_t)n * 2),
+      cnf((size_t)n);
+  std::vector<int32_t> stp((size_t)n * 2);
+  SsfSurfels dst = {pos.data(), col.data(), stp.data(), ori.data(), shp.data(), dms.data(), cnf.data()};
+  rc = copy_set_out(e, e->model, &dst, n);
+  if (rc) return rc;
+  FILE* f = fopen(path, "w");
+  if (!f) { e->err = std::string("cannot open ") + path; return SSF_ERR_IO; }
+  // std::to_string(float) == "%f" (supersurfel_fusion.cu:616-630)
+  for (int i = 0; i < n; i++) {
+    if (!(cnf[i] > e->cfg.conf_thresh)) continue;
+    fprintf(f, "%d %d %f\n", stp[2 * i], stp[2 * i + 1], cnf[i]);
+    fprintf(f, "%f %f %f\n", pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+    fprintf(f, "%f %f %f\n", col[3 * i], col[3 * i + 1], col[3 * i + 2]);
+    fprintf(f, "%f %f\n", dms[2 * i], dms[2 * i + 1]);
+    fprintf(f, "%f %f %f %f %f %f %f %f %f\n", ori[9 * i], ori[9 * i + 1], ori[9 * i + 2], ori[9 * i + 3],
+            ori[9 * i + 4], ori[9 * i + 5], ori[9 * i + 6], ori[9 * i + 7], ori[9 * i + 8]);
+    fprintf(f, "%f %f %f %f %f %f\n", shp[6 * i], shp[6 * i + 1], shp[6 * i + 2], shp[6 * i + 3], shp[6 * i + 4],
+            shp[6 * i + 5]);
+    fprintf(f, "\n");
+  }
+  fclose(f);
+  return SSF_OK;
+}
+
+int ssf_extract_local_point_cloud(SsfHandle h, float radius, float* positions, float* normals, int capacity,
+                                  int* count) {
+  H_CHECK(h);
+  if (!positions || !normals || capacity < 0 || !count) return SSF_ERR_INVALID_ARG;
+  int rc = ensure_scratch(e, (size_t)capacity * 24 + 16);
+  if (rc) return rc;
+  float* dpos = reinterpret_cast<float*>(e->scratch);
+  float* dnrm = dpos + (size_t)capacity * 3;
+  SSF_CUDA(e, cudaMemsetAsync(&e->counters->cloud_count, 0, sizeof(int), e->stream));
+  launch_local_cloud(e, radius, dpos, dnrm, capacity);
+  int n = 0;
+  SSF_CUDA(e, cudaMemcpyAsync(&n, &e->counters->cloud_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (n > capacity) n = capacity;
+  if (n > 0) {
+    SSF_CUDA(e, cudaMemcpyAsync(positions, dpos, (size_t)n * 12, cudaMemcpyDefault, e->stream));
+    SSF_CUDA(e, cudaMemcpyAsync(normals, dnrm, (size_t)n * 12, cudaMemcpyDefault, e->stream));
+    SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  }
+  *count = n;
+  return SSF_OK;
+}
+
+int ssf_invalidate_frame_supersurfels(SsfHandle h, const uint8_t* mask) {
+  H_CHECK(h);
+  if (!mask) return SSF_ERR_INVALID_ARG;
+  int rc = ensure_scratch(e, (size_t)e->S);
+  if (rc) return rc;
+  SSF_CUDA(e, cudaMemcpyAsync(e->scratch, mask, (size_t)e->S, cudaMemcpyDefault, e->stream));
+  launch_invalidate(e, reinterpret_cast<const uint8_t*>(e->scratch));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_transform_model(SsfHandle h, const float R[9], const float t[3]) {
+  H_CHECK(h);
+  launch_transform_model(e, R, t);
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_set_model(SsfHandle h, const SsfSurfels* src, int nb_supersurfels, int nb_visible) {
+  H_CHECK(h);
+  if (nb_supersurfels < 0 || nb_supersurfels > e->cap || nb_visible < 0 || nb_visible > nb_supersurfels)
+    return SSF_ERR_INVALID_ARG;
+  int rc = copy_set_in(e, src, nb_supersurfels, e->model);
+  if (rc) return rc;
+  launch_model_lab(e, nb_supersurfels);
+  int c[2] = {nb_supersurfels, nb_visible};
+  SSF_CUDA(e, cudaMemcpyAsync(&e->counters->nb_supersurfels, c, 2 * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_set_frame(SsfHandle h, const SsfSurfels* src) {
+  H_CHECK(h);
+  int rc = copy_set_in(e, src, e->S, e->frame);
+  if (rc) return rc;
+  launch_frame_tables(e);
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_set_segmentation(SsfHandle h, const int32_t* labels, const int32_t* bound, const uint8_t* inliers,
+                         const float* slanted_depth, const uint8_t* rgba) {
+  H_CHECK(h);
+  const size_t N = e->npix;
+  if (labels) SSF_CUDA(e, cudaMemcpyAsync(e->labels, labels, N * 4, cudaMemcpyDefault, e->stream));
+  if (bound) SSF_CUDA(e, cudaMemcpyAsync(e->bound, bound, N * 4, cudaMemcpyDefault, e->stream));
+  if (inliers) SSF_CUDA(e, cudaMemcpyAsync(e->inliers, inliers, N, cudaMemcpyDefault, e->stream));
+  if (rgba) SSF_CUDA(e, cudaMemcpyAsync(e->rgba, rgba, N * 4, cudaMemcpyDefault, e->stream));
+  if (slanted_depth) {
+    int rc = ensure_scratch(e, N * 4);
+    if (rc) return rc;
+    SSF_CUDA(e, cudaMemcpyAsync(e->scratch, slanted_depth, N * 4, cudaMemcpyDefault, e->stream));
+    launch_build_lmap(e, reinterpret_cast<const float*>(e->scratch));
+  }
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_tps_segment(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth, size_t depth_stride) {
+  H_CHECK(h);
+  if (!rgb || !depth) return SSF_ERR_INVALID_ARG;
+  if (rgb_stride == 0) rgb_stride = (size_t)e->W * 3;
+  if (depth_stride == 0) depth_stride = (size_t)e->W * 4;
+  SSF_CUDA(e, cudaMemcpy2DAsync(e->in_rgb, (size_t)e->W * 3, rgb, rgb_stride, (size_t)e->W * 3, e->H, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpy2DAsync(e->in_depth, (size_t)e->W * 4, depth, depth_stride, (size_t)e->W * 4, e->H, cudaMemcpyDefault, e->stream));
+  launch_ingest(e, e->in_rgb, (size_t)e->W * 3, e->in_depth, (size_t)e->W * 4);
+  launch_tps(e);
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_CUDA(e, cudaGetLastError());
+  return SSF_OK;
+}
+
+int ssf_get_ransac_samples(SsfHandle h, float* samples) {
+  H_CHECK(h);
+  SSF_CUDA(e, cudaMemcpyAsync(samples, e->samples, (size_t)e->S * e->cfg.nb_samples * sizeof(float4), cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_generate_supersurfels(SsfHandle h) {
+  H_CHECK(h);
+  launch_extract(e);
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_CUDA(e, cudaGetLastError());
+  return SSF_OK;
+}
+
+static int resolve_n(EngineImpl* e, int n_src, int* out) {
+  if (n_src <= 0) {
+    int rc = read_report(e, false);
+    if (rc) return rc;
+    n_src = e->h_report->counters.nb_visible;
+  }
+  if (n_src > e->cap) return SSF_ERR_INVALID_ARG;
+  *out = n_src;
+  return SSF_OK;
+}
+
+int ssf_icp_system(SsfHandle h, const float R[9], const float t[3], int n_src, float out29[29]) {
+  H_CHECK(h);
+  if (!R || !t || !out29) return SSF_ERR_INVALID_ARG;
+  int n = 0;
+  int rc = resolve_n(e, n_src, &n);
+  if (rc) return rc;
+  launch_icp_set_transform(e, R, t);
+  if (n > 0) launch_icp_system(e, e->model, nullptr, n, false);
+  else SSF_CUDA(e, cudaMemsetAsync(e->icp->sys, 0, sizeof(float) * 32, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(out29, e->icp->sys, 29 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_CUDA(e, cudaGetLastError());
+  return SSF_OK;
+}
+
+int ssf_icp_system_enqueue(SsfHandle h, const float R[9], const float t[3], int n_src, int launches) {
+  H_CHECK(h);
+  if (!R || !t || launches < 0) return SSF_ERR_INVALID_ARG;
+  int n = 0;
+  int rc = resolve_n(e, n_src, &n);
+  if (rc) return rc;
+  if (n <= 0) return SSF_ERR_STATE;
+  launch_icp_set_transform(e, R, t);
+  for (int i = 0; i < launches; i++) launch_icp_system(e, e->model, nullptr, n, false);
+  SSF_CUDA(e, cudaGetLastError());
+  return SSF_OK;
+}
+
+int ssf_icp(SsfHandle h, const float* R_init, const float* t_init, float out29[29], float R_rel[9], float t_rel[3],
+            int* iters, int* valid) {
+  H_CHECK(h);
+  if ((R_init == nullptr) != (t_init == nullptr)) return SSF_ERR_INVALID_ARG;
+  if (R_init) launch_icp_begin(e, R_init, t_init);
+  else launch_icp_begin_from_pose(e);
+  launch_icp_loop(e);
+  launch_icp_finish(e, false);
+  IcpState* hs = nullptr;
+  SSF_CUDA(e, cudaMallocHost(reinterpret_cast<void**>(&hs), sizeof(IcpState)));
+  cudaError_t err = cudaMemcpyAsync(hs, e->icp, sizeof(IcpState), cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  if (err != cudaSuccess) { cudaFreeHost(hs); e->err = cudaGetErrorString(err); return SSF_ERR_CUDA; }
+  if (out29) memcpy(out29, hs->sys, 29 * sizeof(float));
+  if (R_rel) memcpy(R_rel, hs->Rrel, 36);
+  if (t_rel) memcpy(t_rel, hs->trel, 12);
+  if (iters) *iters = hs->active ? hs->iter : 0;
+  if (valid) *valid = hs->active ? hs->valid : 0;
+  cudaFreeHost(hs);
+  return SSF_OK;
+}
+
+int ssf_fuse(SsfHandle h) {
+  H_CHECK(h);
+  launch_fuse(e);
+  int rc = read_report(e, false);
+  if (rc) return rc;
+  SSF_CUDA(e, cudaGetLastError());
+  fill_stats(e, 0.f);
+  return SSF_OK;
+}
+
+int ssf_timer_start(SsfHandle h) {
+  H_CHECK(h);
+  SSF_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+  return SSF_OK;
+}
+
+int ssf_timer_stop(SsfHandle h, float* ms) {
+  H_CHECK(h);
+  SSF_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+  SSF_CUDA(e, cudaEventSynchronize(e->ev1));
+  if (ms) SSF_CUDA(e, cudaEventElapsedTime(ms, e->ev0, e->ev1));
+  return SSF_OK;
+}
+
+int ssf_synchronize(SsfHandle h) {
+  H_CHECK(h);
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
+}
+
+int ssf_get_launch_count(SsfHandle h, uint64_t* launches) {
+  H_CHECK(h);
+  if (!launches) return SSF_ERR_INVALID_ARG;
+  *launches = e->launches;
+  return SSF_OK;
+}
+
+}  // extern "C"

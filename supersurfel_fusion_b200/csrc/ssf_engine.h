@@ -1,0 +1,165 @@
+// Internal (not exported) declarations of libssf: the engine state that lives in HBM
+// and the stage launchers.  Public surface is include/ssf.h only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/ssf.h"
+
+namespace ssf {
+
+// ---- HBM layout ---------------------------------------------------------------
+// Supersurfel sets (frame: S rows, model: capacity rows) are stored PLANAR: one
+// contiguous float plane per scalar attribute, `stride` elements apart, so that a
+// warp reading attribute k of 32 consecutive supersurfels issues one fully coalesced
+// 128-byte request and a thread reading 4 consecutive supersurfels issues one
+// float4 load.  The reference keeps array-of-float3 / Mat33 / Cov3
+// (supersurfels.hpp:32-41), which strides a warp over 12/36/24-byte records.
+enum Plane {
+  P_POS = 0,      // 3: position
+  P_COL = 3,      // 3: colour, RGB 0..255
+  P_STAMP = 6,    // 2: int stamps (t0, t) bit-cast
+  P_ORI = 8,      // 9: e1, e2, normal
+  P_SHAPE = 17,   // 6: xx xy xz yy yz zz
+  P_DIM = 23,     // 2
+  P_CONF = 25,    // 1
+  P_LAB = 26,     // 3: CIELab of P_COL, derived (hoisted out of the ICP / association loops)
+  P_COUNT = 29
+};
+
+struct SurfelSet {
+  float* base;     // P_COUNT * stride floats
+  int stride;      // elements per plane, multiple of 4 (float4 alignment)
+  __host__ __device__ float* plane(int p) const { return base + (size_t)p * stride; }
+};
+
+// per-superpixel TPS state (reference: SuperpixelRGBD, TPS_RGBD.hpp:33-38)
+struct Superpixel { float4 xy_rg, theta_b, size; };
+// running sums (reference: SuperpixelRGBDCoeffs, TPS_RGBD.hpp:40-44), integer so that
+// atomic accumulation is order-free
+struct SpSums {
+  long long x, y, r, g, b, n;
+  long long dx, dy, dxx, dyy, dxy, dn;
+  long long dxd, dyd, dd;   // 2^-30 fixed point
+  long long pad;
+};
+
+// Gauss-Newton state of one frame-to-model registration, device resident
+struct IcpState {
+  double tf_inc[16];     // accumulated increment (row-major 4x4)
+  double JtJ[36];        // last built system, full symmetric
+  double prev_error, error;
+  float Rinit[9], tinit[3];
+  float Rc[9], tc[3];    // transform the next system build uses (R_corres, t_corres)
+  float tinc_top[3];     // t_inc at the top of the last executed iteration
+  float sys[32];         // last built system (29 used)
+  float Rrel[9], trel[3];
+  float inliers;
+  int iter;              // iterations executed
+  int done;              // loop finished (converged, starved, or budget spent)
+  int valid;
+  int active;            // 0 when there is nothing to register against (bootstrap)
+  unsigned int ticket;   // last-block-done counter
+};
+
+struct Counters {
+  int nb_supersurfels, nb_visible, nb_removed, nb_matched, nb_inserted;
+  int stamp;
+  int cloud_count;
+  int pad;
+};
+
+struct DevicePose { float R[9]; float t[3]; };
+
+struct Engine {
+  SsfConfig cfg;
+  int device;
+  cudaStream_t own_stream, stream;
+  cudaEvent_t ev0, ev1, evf0, evf1;
+  std::string err;
+  uint64_t launches;
+
+  int W, H, S, gx, gy, cap;
+  size_t npix;
+
+  // images
+  uchar4* rgba;
+  float* disp;
+  int* labels;
+  int* bound;
+  unsigned char* inliers;
+  int2* lmap;            // (label, slanted depth bits) interleaved: one 8-byte gather per lookup
+  uint8_t* in_rgb;       // staging for the raw inputs
+  float* in_depth;
+  float* depth_f;        // bilateral-filtered depth (optional ingest)
+
+  // TPS
+  Superpixel* sp;
+  SpSums* sums;
+  float4* samples;
+  void* rng;             // curandState[S * nb_samples]
+  float* filt_a;         // 8 floats per node (X, Z, px, py), double buffered
+  float* filt_b;
+  unsigned long long* xsums;  // extraction accumulators, 16 per superpixel
+
+  // supersurfels
+  SurfelSet frame, model, model_alt;
+  float4* ftab;          // per frame supersurfel: (L,a,b,conf) (nx,ny,nz,0)
+  unsigned char* matched;
+  unsigned long long* best;   // packed (dist bits << 32 | model id) arg-min keys
+  int* states;
+  int* scan_tmp;
+
+  // registration
+  IcpState* icp;
+  float* icp_partials;   // [grid][32]
+  int icp_grid;
+
+  Counters* counters;
+  DevicePose* pose;
+  // pinned host mirrors
+  Counters* h_counters;
+  DevicePose* h_pose;
+  IcpState* h_icp;
+  SsfFrameStats stats;
+
+  void* scratch;         // AoS <-> planar conversion buffer
+  size_t scratch_bytes;
+};
+
+// ---- stage launchers (each enqueues on e->stream, no host sync) -----------------
+void launch_icp_system(Engine* e, const SurfelSet& src, const int* n_dev, int n_host, bool solve);
+void launch_icp_begin(Engine* e, const float* Rinit_or_null, const float* tinit_or_null);  // host ptrs
+void launch_icp_begin_from_pose(Engine* e);
+void launch_icp_set_transform(Engine* e, const float* R, const float* t);
+void launch_icp_loop(Engine* e);
+void launch_icp_finish(Engine* e, bool apply_to_pose);
+void launch_ingest(Engine* e, const uint8_t* rgb_dev, size_t rgb_stride, const float* depth_dev,
+                   size_t depth_stride);
+void launch_tps(Engine* e);
+void launch_extract(Engine* e);
+void launch_fuse(Engine* e);
+void launch_build_lmap(Engine* e, const float* slanted_dev);
+void launch_frame_tables(Engine* e);
+void launch_model_lab(Engine* e, int n);
+void launch_pack(Engine* e, const SurfelSet& set, int n, const SsfSurfels& dst_dev);   // planar -> member layout
+void launch_unpack(Engine* e, const SsfSurfels& src_dev, int n, const SurfelSet& set);
+void launch_transform_model(Engine* e, const float* R, const float* t);
+void launch_local_cloud(Engine* e, float radius, float* pos_dev, float* nrm_dev, int capacity);
+void launch_preview(Engine* e, uint8_t* bgr_dev);
+void launch_invalidate(Engine* e, const uint8_t* mask_dev);
+void tps_init_rng(Engine* e);
+
+#define SSF_CUDA(e, call)                                                            \
+  do {                                                                               \
+    cudaError_t _err = (call);                                                       \
+    if (_err != cudaSuccess) {                                                       \
+      (e)->err = std::string(#call) + ": " + cudaGetErrorString(_err);               \
+      return SSF_ERR_CUDA;                                                           \
+    }                                                                                \
+  } while (0)
+
+}  // namespace ssf
+
+struct SsfEngine : public ssf::Engine {};

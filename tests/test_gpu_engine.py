@@ -1,0 +1,140 @@
+"""GPU parity of the whole per-frame path (processFrame) against the CPU oracle on synthetic
+sequences: poses within 1e-4 m / 1e-4 rad, label maps bit-exact, counts exact, model
+attributes within 1e-4 relative; plus size-independent properties at the full VGA size."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DEFAULT_PARAMS, TUM_PARAMS, make_pair, rel_err, rot_angle
+from supersurfel_fusion_b200.synth import SyntheticSequence
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_pair(orc, seq, params, n_frames, check_every=1):
+    oeng, geng = make_pair(orc, seq, params)
+    worst_t = worst_r = 0.0
+    for k in range(n_frames):
+        rgb, depth = seq.frame(k)
+        so = oeng.process_frame(rgb, depth)
+        sg = geng.processFrame(rgb, depth)
+        for key in ("stamp", "nb_supersurfels", "nb_visible", "nb_removed", "icp_valid", "icp_iters"):
+            assert sg[key] == so[key], (k, key, sg, so)
+        assert sg["icp_inliers"] == so["icp_inliers"], k
+        Ro, to = oeng.pose()
+        Rg, tg = geng.getPose()
+        worst_t = max(worst_t, float(np.linalg.norm(tg - to)))
+        worst_r = max(worst_r, rot_angle(Rg, Ro))
+        if k % check_every == 0:
+            assert np.array_equal(geng.getSegmentation()["labels"], oeng.tps.get()["labels"]), k
+    assert worst_t < 1e-4 and worst_r < 1e-4, (worst_t, worst_r)
+    return oeng, geng
+
+
+def test_sequence_vga_tum_params(orc):
+    seq = SyntheticSequence(seed=1234)
+    oeng, geng = _run_pair(orc, seq, TUM_PARAMS, 12, check_every=3)
+    n = oeng.last["nb_supersurfels"]
+    mo, mg = oeng.model(), geng.getModel(n)
+    assert np.array_equal(mg.stamps, mo.stamps)
+    assert np.array_equal(mg.confidences, mo.confidences)
+    for name in ("positions", "colors", "orientations", "shapes", "dims"):
+        assert rel_err(getattr(mg, name), getattr(mo, name)) < 1e-4, name
+    fo, fg = oeng.frame(), geng.getFrame()
+    assert np.array_equal(fg.confidences, fo.confidences)
+    assert rel_err(fg.positions, fo.positions) < 1e-4
+    # tracking actually follows the ground truth (sanity, not parity)
+    Rg, tg = geng.getPose()
+    Rt, tt = seq.pose(11)
+    assert np.linalg.norm(tg - tt) < 0.03
+
+
+def test_sequence_default_params_small(orc):
+    seq = SyntheticSequence(width=320, height=240, seed=21)
+    _run_pair(orc, seq, DEFAULT_PARAMS, 8)
+
+
+def test_sequence_with_pose_prior(orc):
+    seq = SyntheticSequence(width=320, height=240, seed=4)
+    oeng, geng = make_pair(orc, seq, TUM_PARAMS)
+    for k in range(5):
+        rgb, depth = seq.frame(k)
+        prior = seq.pose(k) if k % 2 else None     # ground truth as the "VO" prior on odd frames
+        so = oeng.process_frame(rgb, depth, prior)
+        sg = geng.processFrame(rgb, depth, pose_prior=prior)
+        assert sg["nb_supersurfels"] == so["nb_supersurfels"]
+        Ro, to = oeng.pose()
+        Rg, tg = geng.getPose()
+        assert np.linalg.norm(tg - to) < 1e-4 and rot_angle(Rg, Ro) < 1e-4
+
+
+def test_strided_and_device_inputs_agree(orc):
+    import torch
+    seq = SyntheticSequence(width=320, height=240, seed=6)
+    _, a = make_pair(orc, seq, TUM_PARAMS)
+    _, b = make_pair(orc, seq, TUM_PARAMS)
+    _, c = make_pair(orc, seq, TUM_PARAMS)
+    for k in range(3):
+        rgb, depth = seq.frame(k)
+        big_rgb = np.zeros((240, 400, 3), np.uint8); big_rgb[:, :320] = rgb
+        big_d = np.zeros((240, 352), np.float32); big_d[:, :320] = depth
+        a.processFrame(rgb, depth)
+        b.processFrame(big_rgb[:, :320], big_d[:, :320])          # strided host views
+        c.processFrameDevice(torch.from_numpy(rgb).cuda(), torch.from_numpy(depth).cuda())
+        torch.cuda.synchronize()
+    for other in (b, c):
+        assert np.array_equal(a.getSegmentation()["labels"], other.getSegmentation()["labels"])
+        assert np.array_equal(a.getPose()[1], other.getPose()[1])
+        assert a.getCounts() == other.getCounts()
+
+
+def test_full_size_properties():
+    """Size-independent invariants at 640x480 and 1280x960 (no oracle involved)."""
+    from supersurfel_fusion_b200 import CamParam, SupersurfelFusion
+    for (w, h) in ((640, 480), (1280, 960)):
+        seq = SyntheticSequence(width=w, height=h, seed=1234)
+        eng = SupersurfelFusion().initialize(CamParam(*seq.cam_param()), **dict(TUM_PARAMS, seg_use_ransac=True))
+        rgb, depth = seq.frame(0)
+        eng.processFrame(rgb, depth)
+        seg = eng.getSegmentation()
+        L, B = seg["labels"], seg["bound"]
+        S = eng.nbSuperpixels
+        assert L.min() >= 0 and L.max() < S
+        # per-superpixel pixel counts equal the running sums' n, means equal recomputed means
+        cnt = np.bincount(L.ravel(), minlength=S)
+        assert np.array_equal(cnt.astype(np.float32), seg["superpixels"][:, 8])
+        ys, xs = np.mgrid[0:h, 0:w]
+        mx = np.bincount(L.ravel(), weights=xs.ravel(), minlength=S) / np.maximum(cnt, 1)
+        assert np.abs(mx - seg["superpixels"][:, 0])[cnt > 0].max() < 1e-3
+        # boundary counts are exactly the number of differing 4-neighbours (image border counts)
+        pad = np.pad(L, 1, constant_values=-1)
+        nb = ((pad[:-2, 1:-1] != L).astype(np.int32) + (pad[2:, 1:-1] != L) + (pad[1:-1, :-2] != L) + (pad[1:-1, 2:] != L))
+        assert (nb == B).mean() > 0.995       # the reference's stale-snapshot updates leave rare off-by-ones
+        # determinism: a second engine on the same input gives identical bits
+        eng2 = SupersurfelFusion().initialize(CamParam(*seq.cam_param()), **dict(TUM_PARAMS, seg_use_ransac=True))
+        eng2.processFrame(rgb, depth)
+        assert np.array_equal(eng2.getSegmentation()["labels"], L)
+        f1, f2 = eng.getFrame(), eng2.getFrame()
+        assert np.array_equal(f1.positions.view(np.uint32), f2.positions.view(np.uint32))
+        # idempotence of the frame pipeline w.r.t. the model: bootstrap copies the frame
+        m = eng.getModel()
+        assert m.n == S and np.array_equal(m.positions, f1.positions)
+
+
+def test_export_model_format(orc, tmp_path):
+    seq = SyntheticSequence(width=320, height=240, seed=4)
+    _, geng = make_pair(orc, seq, dict(TUM_PARAMS, conf_thresh=400.0))
+    for k in range(4):
+        geng.processFrame(*seq.frame(k))
+    path = os.path.join(str(tmp_path), "model.txt")
+    geng.exportModel(path)
+    blocks = [b for b in open(path).read().split("\n\n") if b.strip()]
+    m = geng.getModel()
+    assert len(blocks) == int((m.confidences > 400.0).sum()) > 0
+    first = blocks[0].split("\n")
+    assert [len(l.split()) for l in first] == [3, 3, 3, 2, 9, 6]   # supersurfel_fusion.cu:616-630
+    pos, nrm = geng.extractLocalPointCloud()
+    assert len(pos) == int((m.confidences >= 400.0).sum()) or len(pos) <= m.n
+    assert geng.computeSuperpixelSegIm().shape == (240, 320, 3)
+    assert np.array_equal(geng.computeSlantedPlaneIm(), geng.getSegmentation()["slanted"])
