@@ -74,5 +74,19 @@ def rel_err(a, b):
 
 
 def rot_angle(Ra, Rb):
-    c = (np.trace(np.asarray(Ra, np.float64).T @ np.asarray(Rb, np.float64)) - 1.0) / 2.0
-    return float(np.arccos(np.clip(c, -1.0, 1.0)))
+    """Angle of Ra^T Rb.  atan2 of the skew part: arccos(trace) cannot resolve angles below
+    ~5e-4 rad when the matrices are fp32."""
+    d = np.asarray(Ra, np.float64).T @ np.asarray(Rb, np.float64)
+    s = 0.5 * np.array([d[2, 1] - d[1, 2], d[0, 2] - d[2, 0], d[1, 0] - d[0, 1]])
+    return float(np.arctan2(np.linalg.norm(s), (np.trace(d) - 1.0) / 2.0))
+
+
+def same_floats(a, b):
+    """Bit-identical fp32 arrays, except that any NaN matches any NaN (the device produces the
+    canonical 0x7FFFFFFF, x86 SSE produces 0xFFC00000: NaN payloads are not arithmetic results)."""
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    if a.shape != b.shape:
+        return False
+    both_nan = np.isnan(a) & np.isnan(b)
+    return bool(np.all(both_nan | (a.view(np.uint32) == b.view(np.uint32))))

@@ -4,7 +4,7 @@ results within the tolerance written next to each assert (north_star: 1e-4 relat
 import numpy as np
 import pytest
 
-from conftest import DEFAULT_PARAMS, TUM_PARAMS, make_pair, rel_err, rot_angle
+from conftest import DEFAULT_PARAMS, TUM_PARAMS, make_pair, rel_err, rot_angle, same_floats
 from supersurfel_fusion_b200 import Supersurfels
 from supersurfel_fusion_b200.synth import SyntheticSequence, synthetic_icp_problem
 
@@ -46,15 +46,15 @@ def test_tps_labels_bit_exact(orc, params, seed, size):
         o = oeng.tps.compute(rgb, depth)
         g = geng.tpsSegment(rgb, depth)
         assert np.array_equal(g["rgba"], o["rgba"])
-        assert np.array_equal(g["disp"].view(np.uint32), o["disp"].view(np.uint32))
+        assert same_floats(g["disp"], o["disp"])
         assert np.array_equal(g["labels"], o["labels"]), "label map differs in %d pixels" % (g["labels"] != o["labels"]).sum()
         assert np.array_equal(g["bound"], o["bound"])
         assert np.array_equal(g["inliers"], o["inliers"])
         # RANSAC candidates use the same cuRAND XORWOW streams: identical planes and votes
-        assert np.array_equal(geng.getRansacSamples().view(np.uint32), oeng.tps.samples().view(np.uint32))
+        assert same_floats(geng.getRansacSamples(), oeng.tps.samples())
         # means / planes / slanted depth: same IEEE operations => identical bits
-        assert np.array_equal(g["superpixels"].view(np.uint32), o["superpixels"].view(np.uint32))
-        assert np.array_equal(g["slanted"].view(np.uint32), o["slanted"].view(np.uint32))
+        assert same_floats(g["superpixels"], o["superpixels"])
+        assert same_floats(g["slanted"], o["slanted"])
 
 
 def test_tps_no_ransac_and_odd_iters(orc):
@@ -66,7 +66,7 @@ def test_tps_no_ransac_and_odd_iters(orc):
     g = geng.tpsSegment(rgb, depth)
     assert np.array_equal(g["labels"], o["labels"])
     assert np.array_equal(g["inliers"], o["inliers"])
-    assert np.array_equal(g["superpixels"].view(np.uint32), o["superpixels"].view(np.uint32))
+    assert same_floats(g["superpixels"], o["superpixels"])
 
 
 def test_tps_all_depth_missing(orc):
