@@ -249,9 +249,9 @@ def run_ours(args, rank, world, local_rank):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    roof = icp_roofline(dev, peaks) if world == 1 else None
+    roof = icp_roofline(dev, peaks) if (world == 1 and not args.skip_extras) else None
     cpu = None
-    if world == 1:
+    if world == 1 and not args.skip_extras:
         fps_cpu, dt = time_cpu_oracle(frames, cam, 60)
         cpu = {"value": fps_cpu, "unit": "frames/s", "cores": 1, "kind": "port",
                "sample": "60 frames of the workload sequence (%.1f s of CPU work), CPU oracle restatement, 1 thread" % dt}
@@ -287,13 +287,18 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-extras", action="store_true", help="frames only: no roofline / cpu_baseline legs (for ncu)")
+    ap.add_argument("--roofline-only", action="store_true", help="only the ICP roofline leg (for ncu --set full)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.roofline_only:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        print(json.dumps(icp_roofline(local_rank, peaks)))
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)
