@@ -66,3 +66,15 @@ def test_product_does_not_import_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "liboracle" not in src and "import oracle" not in src and "from oracle" not in src, f
                 assert '#include "oracle' not in src and "#include <oracle" not in src, f
+
+
+def test_cpp_shim_compiles_and_links(ssf_lib_path, tmp_path):
+    """include/supersurfel_fusion.hpp: the reference's class/method names over the C-ABI."""
+    import subprocess
+    src = tmp_path / "shim.cpp"
+    src.write_text('#include "supersurfel_fusion.hpp"\n'
+                   "int main() { supersurfel_fusion::SupersurfelFusion f; return f.isInitialized() ? 1 : 0; }\n")
+    exe = tmp_path / "shim"
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           ssf_lib_path, "-Wl,-rpath," + os.path.dirname(ssf_lib_path)])
+    assert subprocess.call([str(exe)]) == 0
