@@ -7,6 +7,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -190,7 +191,12 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   cudaGetDeviceProperties(&prop, device);
   const int sms = prop.multiProcessorCount;
   const int need_blocks = (e->cap + 1023) / 1024;
-  e->icp_grid = need_blocks < 2 * sms ? need_blocks : 2 * sms;
+  e->icp_occ = 2;
+  if (const char* v = getenv("SSF_ICP_OCC")) e->icp_occ = atoi(v);   // tuning knob: 2, 3 or 4
+  if (e->icp_occ < 2 || e->icp_occ > 4) e->icp_occ = 2;
+  e->icp_debug = 0;
+  if (const char* v = getenv("SSF_ICP_DEBUG")) e->icp_debug = atoi(v);
+  e->icp_grid = need_blocks < e->icp_occ * sms ? need_blocks : e->icp_occ * sms;
 
   cudaError_t err = cudaSuccess;
 #define A(call) if (err == cudaSuccess) err = (call)

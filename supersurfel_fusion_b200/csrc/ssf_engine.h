@@ -115,6 +115,8 @@ struct Engine {
   IcpState* icp;
   float* icp_partials;   // [grid][32]
   int icp_grid;
+  int icp_occ;           // resident CTAs per SM the system kernel is compiled for
+  int icp_debug;         // profiling knob, see IcpArgs::debug
 
   Counters* counters;
   DevicePose* pose;

@@ -189,7 +189,7 @@ def test_icp_large_problem_matches_oracle(orc):
     want = orc.icp_system(cam, prob["src_pos"], prob["src_col"], prob["src_ori"], prob["tgt_col"], prob["tgt_ori"],
                           prob["tgt_conf"], R, t, prob["labels"], prob["depth"])
     got = eng.icpSystem(R, t, len(prob["src_pos"]))
-    assert 0.4 < want[28] / len(prob["src_pos"]) < 0.75
+    assert 0.5 < want[28] / len(prob["src_pos"]) < 0.75
     # borderline gate decisions can differ in a handful of elements out of 6e5 (GPU powf/cbrtf vs libm)
     assert abs(got[28] - want[28]) <= 3
     assert rel_err(got, want) < FP_TOL
