@@ -17,6 +17,8 @@ namespace ssf {
 
 void launch_icp_set_transform(Engine* e, const float* R, const float* t);
 size_t tps_rng_state_bytes();
+size_t tps_trace_bytes(int grid);
+int tps_persistent_grid(int device, int gx, int gy, int cell, int height, int nb_iters, int* cache_slots);
 
 struct FrameReport {
   Counters counters;
@@ -194,6 +196,13 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   e->icp_occ = 2;
   if (const char* v = getenv("SSF_ICP_OCC")) e->icp_occ = atoi(v);   // tuning knob: 2, 3 or 4
   if (e->icp_occ < 2 || e->icp_occ > 4) e->icp_occ = 2;
+  e->tps_grid = tps_persistent_grid(device, e->gx, e->gy, cfg->cell_size, e->H, cfg->seg_iter, &e->tps_cache_slots);
+  // The one-kernel (cooperative, band-owned) form of the segmentation is kept as an option:
+  // measured on B200 at VGA it is ~8 % slower per frame than the graph of small kernels
+  // (per pass: ~1.2 us cache fill + ~4 us relabel + ~1.2 us barrier vs ~7 us for two graph
+  // nodes), see DESIGN.md section 7.
+  e->tps_persistent = 0;
+  if (const char* v = getenv("SSF_TPS_PERSISTENT")) e->tps_persistent = (atoi(v) != 0 && e->tps_grid > 0) ? 1 : 0;
   e->icp_debug = 0;
   if (const char* v = getenv("SSF_ICP_DEBUG")) e->icp_debug = atoi(v);
   e->icp_grid = need_blocks < e->icp_occ * sms ? need_blocks : e->icp_occ * sms;
@@ -218,6 +227,12 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   }
   A(dalloc(&e->filt_a, (size_t)S * 8)); A(dalloc(&e->filt_b, (size_t)S * 8));
   A(dalloc(&e->xsums, (size_t)S * 16));
+  A(dalloc(&e->tps_barrier, (size_t)32));
+  if (getenv("SSF_TPS_TRACE") && e->tps_grid > 0) {
+    char* t = nullptr;
+    A(dalloc(&t, tps_trace_bytes(e->tps_grid)));
+    e->tps_trace = reinterpret_cast<unsigned long long*>(t);
+  }
   e->frame.stride = round4(S);
   e->model.stride = e->model_alt.stride = round4(e->cap);
   A(dalloc(&e->frame.base, (size_t)P_COUNT * e->frame.stride));
@@ -256,7 +271,7 @@ int ssf_destroy(SsfHandle h) {
   cudaDeviceSynchronize();
   if (e->graph_ready) cudaGraphExecDestroy(e->graph_exec);
   void* bufs[] = {e->rgba, e->disp, e->labels, e->bound, e->inliers, e->lmap, e->in_rgb, e->in_depth, e->sp, e->sums,
-                  e->samples, e->rng, e->filt_a, e->filt_b, e->xsums, e->frame.base, e->model.base,
+                  e->samples, e->rng, e->filt_a, e->filt_b, e->xsums, e->tps_barrier, e->tps_trace, e->frame.base, e->model.base,
                   e->model_alt.base, e->ftab, e->matched, e->best, e->states, e->scan_tmp, e->icp, e->icp_partials,
                   e->counters, e->pose, e->d_report, e->scratch};
   for (void* b : bufs)
@@ -604,6 +619,12 @@ int ssf_tps_segment(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const fl
   launch_tps(e);
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   SSF_CUDA(e, cudaGetLastError());
+  if (e->tps_trace) {   // profiling aid: dump the per-CTA phase timestamps of this call
+    std::vector<unsigned long long> host(tps_trace_bytes(e->tps_grid) / 8);
+    cudaMemcpy(host.data(), e->tps_trace, host.size() * 8, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(getenv("SSF_TPS_TRACE"), "wb")) { fwrite(host.data(), 8, host.size(), f); fclose(f); }
+    cudaMemset(e->tps_trace, 0, host.size() * 8);
+  }
   return SSF_OK;
 }
 

@@ -101,6 +101,11 @@ struct Engine {
   void* rng;             // curandState[S * nb_samples]
   float* filt_a;         // 8 floats per node (X, Z, px, py), double buffered
   float* filt_b;
+  int tps_persistent;    // 1: whole segmentation is one cooperative kernel
+  int tps_grid;          // its grid (one CTA per SM)
+  unsigned int* tps_barrier;   // ticket of its grid-wide barrier
+  int tps_cache_slots;   // superpixels its per-CTA shared-memory cache holds
+  unsigned long long* tps_trace;   // profiling aid (SSF_TPS_TRACE=<file>), normally NULL
   unsigned long long* xsums;  // extraction accumulators, 16 per superpixel
 
   // supersurfels

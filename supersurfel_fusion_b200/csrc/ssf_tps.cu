@@ -26,7 +26,10 @@
 #include "ssf_engine.h"
 #include "ssf_math.cuh"
 
+#include <cooperative_groups.h>
 #include <curand_kernel.h>
+
+namespace cg = cooperative_groups;
 
 namespace ssf {
 
@@ -37,6 +40,7 @@ struct TpsArgs {
   int W, H, cell, gx, gy, S;
   int raw_w, raw_h;        // thread extents of the reference launch (TPS_RGBD.cu:185-186)
   int min_size;
+  int debug;               // profiling knob, 0 in production
   float lambda_pos, lambda_bound, lambda_size, lambda_disp, thresh_disp;
   uchar4* rgba;
   float* disp;
@@ -53,6 +57,8 @@ static TpsArgs tps_args(const Engine* e) {
   a.raw_w = 16 * ((e->W / 2 + 15) / 16);
   a.raw_h = 16 * ((e->H / 2 + 15) / 16);
   a.min_size = (int)((float)(e->cfg.cell_size * e->cfg.cell_size) / 4.f);
+  a.debug = 0;
+  if (const char* v = getenv("SSF_TPS_DEBUG")) a.debug = atoi(v);
   a.lambda_pos = e->cfg.lambda_pos; a.lambda_bound = e->cfg.lambda_bound; a.lambda_size = e->cfg.lambda_size;
   a.lambda_disp = e->cfg.lambda_disp; a.thresh_disp = e->cfg.thresh_disp;
   a.rgba = e->rgba; a.disp = e->disp; a.labels = e->labels; a.bound = e->bound; a.inliers = e->inliers;
@@ -135,15 +141,13 @@ __device__ __forceinline__ bool solve_plane(float& tx, float& ty, float& tz, con
   return true;
 }
 
+// means (and, with DISP, the least-squares disparity plane) of one superpixel from its sums
 template <bool DISP>
-__global__ void tps_merge_kernel(TpsArgs a) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.S) return;
-  const SpSums c = a.sums[k];
+__device__ __forceinline__ Superpixel tps_superpixel_from_sums(const SpSums& c) {
   const float n = (float)c.n;
-  Superpixel& s = a.sp[k];
+  Superpixel s;
   s.xy_rg = make_float4((float)c.x / n, (float)c.y / n, (float)c.r / n, (float)c.g / n);
-  s.size.x = n;
+  s.size = make_float4(n, 0.f, 0.f, 0.f);
   const float mb = (float)c.b / n;
   if (DISP) {
     const float dx = (float)c.dx, dy = (float)c.dy, dxx = (float)c.dxx, dyy = (float)c.dyy, dxy = (float)c.dxy,
@@ -157,8 +161,46 @@ __global__ void tps_merge_kernel(TpsArgs a) {
     }
     s.theta_b = make_float4(tx, ty, tz, mb);
   } else {
-    s.theta_b.w = mb;
+    s.theta_b = make_float4(0.f, 0.f, 0.f, mb);   // the plane is unused (and zero) in the colour-only phase
   }
+  return s;
+}
+
+template <bool DISP>
+__device__ __forceinline__ void tps_merge_item(const TpsArgs& a, int k) {
+  const Superpixel n = tps_superpixel_from_sums<DISP>(a.sums[k]);
+  Superpixel& s = a.sp[k];
+  s.xy_rg = n.xy_rg;
+  s.size.x = n.size.x;
+  if (DISP) s.theta_b = n.theta_b;
+  else s.theta_b.w = n.theta_b.w;
+}
+
+// Where a pass reads superpixel means from.  Global: the array the merge phase wrote.
+struct SpGlobal {
+  const Superpixel* sp;
+  __device__ __forceinline__ Superpixel get(int k) const { return sp[k]; }
+};
+// Band cache: the CTA recomputed, from the sums, the superpixels seeded in the grid-cell
+// rows around its band of image rows into shared memory (anything
+// outside the window is recomputed on the fly; the window is sized so that this cannot
+// happen, see the margin in tps_persistent_kernel).
+template <bool DISP>
+struct SpCached {
+  const Superpixel* cache;
+  const SpSums* sums;
+  int first, count;   // cached superpixel ids [first, first + count)
+  __device__ __forceinline__ Superpixel get(int k) const {
+    const int slot = k - first;
+    if (slot >= 0 && slot < count) return cache[slot];
+    return tps_superpixel_from_sums<DISP>(sums[k]);
+  }
+};
+
+template <bool DISP>
+__global__ void tps_merge_kernel(TpsArgs a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < a.S) tps_merge_item<DISP>(a, k);
 }
 
 // ---- one relabelling pass (TPS_RGBD_kernels.cuh:235-651) ---------------------------
@@ -167,20 +209,37 @@ struct Decision {
   unsigned char inlier, prev_inlier;
 };
 
+// Per-pixel inputs of a decision, fetched together with the label window so that all the
+// global loads of a pass are in flight at once (one dependent L2 round trip, not three).
+struct PixelIn {
+  int bounds;
+  uchar4 col;
+  float disp;
+  unsigned char inlier;
+};
 template <bool DISP>
-__device__ __forceinline__ void tps_decide(const TpsArgs& a, int x, int y, const int (&L)[3][4], int c, Decision& d,
-                                           float& disp_v) {
-  const size_t p = (size_t)y * a.W + x;
-  const int bounds = a.bound[p];
+__device__ __forceinline__ PixelIn tps_fetch_pixel(const TpsArgs& a, size_t p) {
+  PixelIn in;
+  in.bounds = a.bound[p];
+  in.col = a.rgba[p];
+  in.disp = DISP ? a.disp[p] : 0.f;
+  in.inlier = DISP ? a.inliers[p] : (unsigned char)0;
+  return in;
+}
+
+template <bool DISP, typename SP>
+__device__ __forceinline__ void tps_decide(const TpsArgs& a, const SP& spsrc, const PixelIn& in, int x, int y,
+                                           const int (&L)[3][4], int c, Decision& d, float& disp_v) {
+  const int bounds = in.bounds;
   const int index = L[1][c];
   int new_index = index;
-  const Superpixel prev = a.sp[index];
+  const Superpixel prev = spsrc.get(index);
   unsigned char inlier = 0xff, prev_inlier = 0;
   float disp_energy = 0.f;
   disp_v = 0.f;
   if (DISP) {
-    disp_v = a.disp[p];
-    prev_inlier = a.inliers[p];
+    disp_v = in.disp;
+    prev_inlier = in.inlier;
     const float dp = prev.theta_b.x * (float)x + prev.theta_b.y * (float)y + prev.theta_b.z;
     disp_energy = (dp - disp_v) * (dp - disp_v);
     if (!isfinite(disp_energy) || disp_energy > a.thresh_disp || dp < 0.f) {
@@ -203,7 +262,7 @@ __device__ __forceinline__ void tps_decide(const TpsArgs& a, int x, int y, const
     movable = !(jump > 2);
   }
   if (movable) {
-    const uchar4 col = a.rgba[p];
+    const uchar4 col = in.col;
     const float cr = (float)col.x, cg = (float)col.y, cb = (float)col.z;
     const float px = (float)x, py = (float)y;
     const float size = prev.size.x;
@@ -216,11 +275,16 @@ __device__ __forceinline__ void tps_decide(const TpsArgs& a, int x, int y, const
     best = best - a.lambda_size * fminf(dsize, 0.f);
     best = best + a.lambda_bound * (float)bounds;
     const int nl[4] = {L[0][c], L[1][c - 1], L[1][c + 1], L[2][c]};  // up, left, right, down
+    // the four candidates are evaluated as independent straight-line chains (so that they
+    // overlap in the pipeline) and then compared in the reference's order: up, left, right, down
+    float cand_e[4];
+    unsigned char cand_in[4];
+    bool cand_ok[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int i_n = nl[k];
-      if (i_n == -1 || i_n == index) continue;
-      const Superpixel ns = a.sp[i_n];
+      cand_ok[k] = !(i_n == -1 || i_n == index);
+      const Superpixel ns = spsrc.get(cand_ok[k] ? i_n : index);
       const float ex = px - ns.xy_rg.x, ey = py - ns.xy_rg.y;
       const float fx = cr - ns.xy_rg.z, fy = cg - ns.xy_rg.w, fz = cb - ns.theta_b.w;
       const float nsize = ns.size.x + 1.f - (float)a.min_size;
@@ -229,10 +293,9 @@ __device__ __forceinline__ void tps_decide(const TpsArgs& a, int x, int y, const
       if (DISP) {
         const float dp = ns.theta_b.x * (float)x + ns.theta_b.y * (float)y + ns.theta_b.z;
         n_energy = (dp - disp_v) * (dp - disp_v);
-        if (!isfinite(n_energy) || n_energy > a.thresh_disp || dp < 0.f) {
-          n_energy = a.thresh_disp;
-          n_inlier = 0;
-        }
+        const bool out = !isfinite(n_energy) || n_energy > a.thresh_disp || dp < 0.f;
+        n_energy = out ? a.thresh_disp : n_energy;
+        n_inlier = out ? 0 : 0xff;
       }
       int b = 0;
 #pragma unroll
@@ -241,10 +304,15 @@ __device__ __forceinline__ void tps_decide(const TpsArgs& a, int x, int y, const
       if (DISP) energy = energy + a.lambda_disp * n_energy;
       energy = energy - a.lambda_size * fminf(nsize, 0.f);
       energy = energy + a.lambda_bound * (float)b;
-      if (energy < best) {
-        best = energy;
-        new_index = i_n;
-        if (DISP) inlier = n_inlier;
+      cand_e[k] = energy;
+      cand_in[k] = n_inlier;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (cand_ok[k] && cand_e[k] < best) {
+        best = cand_e[k];
+        new_index = nl[k];
+        if (DISP) inlier = cand_in[k];
       }
     }
     if (new_index != index) {
@@ -255,10 +323,8 @@ __device__ __forceinline__ void tps_decide(const TpsArgs& a, int x, int y, const
   d.index = index; d.new_index = new_index; d.b = newb; d.inlier = inlier; d.prev_inlier = prev_inlier;
 }
 
-template <bool DISP>
-__global__ void __launch_bounds__(128) tps_pass_kernel(TpsArgs a, int OX, int OY) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;   // pair index along the row
-  const int ry = blockIdx.y * blockDim.y + threadIdx.y;
+template <bool DISP, typename SP>
+__device__ __forceinline__ void tps_pass_item(const TpsArgs& a, const SP& spsrc, int q, int ry, int OX, int OY) {
   const int y = 2 * ry + OY;
   if (ry >= a.raw_h || y >= a.H || 32 * (ry / 16) + OY >= a.H) return;
   const int rx0 = OX ? 2 * q : 2 * q - 1;
@@ -285,9 +351,13 @@ __global__ void __launch_bounds__(128) tps_pass_kernel(TpsArgs a, int OX, int OY
   }
   Decision d[2];
   float dv[2];
+  PixelIn pin[2];
 #pragma unroll
   for (int j = 0; j < 2; j++)
-    if (ok[j]) tps_decide<DISP>(a, xs[j], y, L, 1 + j, d[j], dv[j]);
+    if (ok[j]) pin[j] = tps_fetch_pixel<DISP>(a, (size_t)y * a.W + xs[j]);
+#pragma unroll
+  for (int j = 0; j < 2; j++)
+    if (ok[j]) tps_decide<DISP>(a, spsrc, pin[j], xs[j], y, L, 1 + j, d[j], dv[j]);
 
   // apply (reads above are all pass-start values: only this thread writes them)
   int partner_delta[2] = {0, 0};
@@ -311,7 +381,7 @@ __global__ void __launch_bounds__(128) tps_pass_kernel(TpsArgs a, int OX, int OY
         if (is_partner) partner_delta[1 - j] += delta;
         else atomicAdd(&a.bound[(size_t)(y + nys[k]) * a.W + (x + nxs[k])], delta);
       }
-      const uchar4 col = a.rgba[p];
+      const uchar4 col = pin[j].col;
       SpSums* o = &a.sums[d[j].index];
       SpSums* n = &a.sums[d[j].new_index];
       add64(&o->x, -x); add64(&o->y, -y); add64(&o->r, -(int)col.x); add64(&o->g, -(int)col.y);
@@ -348,6 +418,100 @@ __global__ void __launch_bounds__(128) tps_pass_kernel(TpsArgs a, int OX, int OY
   }
 }
 
+template <bool DISP>
+__global__ void __launch_bounds__(128) tps_pass_kernel(TpsArgs a, int OX, int OY) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;   // pair index along the row
+  const int ry = blockIdx.y * blockDim.y + threadIdx.y;
+  const SpGlobal src = {a.sp};
+  tps_pass_item<DISP>(a, src, q, ry, OX, OY);
+}
+
+// One lane per active pixel (the persistent kernel's form of a pass): the two pixels of an
+// adjacent pair sit in neighbouring lanes and exchange what the pair-per-thread form keeps
+// in registers (the partner's validity and the boundary delta meant for it) by shuffles.
+// Every lane of the warp must call this; out-of-range lanes pass in_range = false.
+template <bool DISP, typename SP>
+__device__ __forceinline__ void tps_pass_pixel(const TpsArgs& a, const SP& spsrc, int q, int j, int ry, int OX,
+                                               int OY, bool in_range) {
+  const int y = 2 * ry + OY;
+  const int rx = (OX ? 2 * q : 2 * q - 1) + j;
+  const int x = 2 * rx + ((rx + OX) & 1);
+  const bool ok = in_range && ry < a.raw_h && y < a.H && 32 * (ry / 16) + OY < a.H && rx >= 0 && rx < a.raw_w &&
+                  32 * (rx / 16) < a.W && x < a.W;
+  int L[3][4];
+  Decision d;
+  PixelIn pin;
+  pin.col = make_uchar4(0, 0, 0, 0);
+  float dv = 0.f;
+  d.index = d.new_index = -1; d.b = 0; d.inlier = d.prev_inlier = 0;
+  if (ok) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int yy = y - 1 + r;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const int xx = x - 1 + c;
+        L[r][c] = (xx >= 0 && xx < a.W && yy >= 0 && yy < a.H) ? a.labels[(size_t)yy * a.W + xx] : -1;
+      }
+      L[r][3] = -1;
+    }
+    pin = tps_fetch_pixel<DISP>(a, (size_t)y * a.W + x);
+    if (a.debug != 2) tps_decide<DISP>(a, spsrc, pin, x, y, L, 1, d, dv);
+  }
+  // all pass-start reads of the warp are done before any lane writes
+  __syncwarp();
+  const bool partner_ok = __shfl_xor_sync(0xffffffffu, ok ? 1 : 0, 1) != 0;
+  const bool moved = ok && d.new_index != d.index && a.debug != 1;
+  const size_t p = ok ? (size_t)y * a.W + x : 0;
+  int to_partner = 0;
+  if (moved) {
+    const int nxs[4] = {0, -1, 1, 0}, nys[4] = {-1, 0, 0, 1};
+    const int nl[4] = {L[0][1], L[1][0], L[1][2], L[2][1]};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int i_n = nl[k];
+      int delta = 0;
+      if (i_n == d.new_index) delta = -1;
+      else if (i_n == d.index) delta = 1;
+      if (delta == 0 || i_n == -1) continue;
+      const bool is_partner = partner_ok && ((j == 0 && k == 2) || (j == 1 && k == 1));
+      if (is_partner) to_partner += delta;
+      else atomicAdd(&a.bound[(size_t)(y + nys[k]) * a.W + (x + nxs[k])], delta);
+    }
+    const uchar4 col = pin.col;
+    SpSums* o = &a.sums[d.index];
+    SpSums* n = &a.sums[d.new_index];
+    add64(&o->x, -x); add64(&o->y, -y); add64(&o->r, -(int)col.x); add64(&o->g, -(int)col.y);
+    add64(&o->b, -(int)col.z); add64(&o->n, -1);
+    add64(&n->x, x); add64(&n->y, y); add64(&n->r, col.x); add64(&n->g, col.y); add64(&n->b, col.z);
+    add64(&n->n, 1);
+    a.labels[p] = d.new_index;
+  }
+  if (DISP && ok && a.debug != 1) {
+    const unsigned char inl = d.inlier, pin = d.prev_inlier;
+    if (inl && (!pin || moved)) {
+      SpSums* s = &a.sums[d.new_index];
+      const long long qd = quantize(dv, kDispFix, kDispClamp);
+      add64(&s->dx, x); add64(&s->dy, y); add64(&s->dxx, (long long)x * x); add64(&s->dyy, (long long)y * y);
+      add64(&s->dxy, (long long)x * y); add64(&s->dxd, (long long)x * qd); add64(&s->dyd, (long long)y * qd);
+      add64(&s->dd, qd); add64(&s->dn, 1);
+    }
+    if (pin && (!inl || moved)) {
+      SpSums* s = &a.sums[d.index];
+      const long long qd = quantize(dv, kDispFix, kDispClamp);
+      add64(&s->dx, -x); add64(&s->dy, -y); add64(&s->dxx, -(long long)x * x); add64(&s->dyy, -(long long)y * y);
+      add64(&s->dxy, -(long long)x * y); add64(&s->dxd, -(long long)x * qd); add64(&s->dyd, -(long long)y * qd);
+      add64(&s->dd, -qd); add64(&s->dn, -1);
+    }
+    if (inl != pin) a.inliers[p] = inl;
+  }
+  const int from_partner = __shfl_xor_sync(0xffffffffu, to_partner, 1);
+  if (ok) {
+    if (moved) a.bound[p] = d.b;                              // own "= b" wins
+    else if (from_partner != 0) a.bound[p] += from_partner;   // only the pair touches it
+  }
+}
+
 // ---- RANSAC plane initialisation (TPS_RGBD_kernels.cu:318-467, 112-190) --------------
 __global__ void tps_rng_init_kernel(curandState* states, int n) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -361,10 +525,9 @@ __device__ __forceinline__ float tex_disp(const TpsArgs& a, float x, float y) {
   return a.disp[(size_t)tex_coord(y, a.H) * a.W + tex_coord(x, a.W)];
 }
 
-__global__ void tps_init_samples_kernel(TpsArgs a, float4* samples, int* votes, curandState* states, int nbWalks,
-                                        float radius) {
-  const int index = blockIdx.x;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void tps_init_sample_item(const TpsArgs& a, float4* samples, int* votes,
+                                                     curandState* states, int nbWalks, float radius, int index,
+                                                     int idx) {
   curandState rnd = states[idx];
   const float cx = a.sp[index].xy_rg.x, cy = a.sp[index].xy_rg.y;
   float x = cx, y = cy;
@@ -403,16 +566,21 @@ __global__ void tps_init_samples_kernel(TpsArgs a, float4* samples, int* votes, 
   states[idx] = rnd;
 }
 
-// evalSamples_kernel: integer votes, aggregated per warp over lanes that share a label
-__global__ void tps_eval_samples_kernel(TpsArgs a, const float4* __restrict__ samples, int* votes, int nbSamples) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+__global__ void tps_init_samples_kernel(TpsArgs a, float4* samples, int* votes, curandState* states, int nbWalks,
+                                        float radius) {
+  tps_init_sample_item(a, samples, votes, states, nbWalks, radius, blockIdx.x, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// evalSamples_kernel: integer votes, aggregated per warp over lanes that share a label.
+// One warp handles 32 consecutive pixels of a row; all 32 lanes must call it.
+__device__ __forceinline__ void tps_eval_row_item(const TpsArgs& a, const float4* samples, int* votes, int nbSamples,
+                                                  int x, int y) {
   const bool in = (x < a.W && y < a.H);
   const size_t p = in ? (size_t)y * a.W + x : 0;
   const int index = in ? a.labels[p] : -1;
   const float d = in ? a.disp[p] : 0.f;
   const unsigned grp = __match_any_sync(0xffffffffu, index);
-  const int lane = threadIdx.x & 31;   // blockDim.x == 32
+  const int lane = threadIdx.x & 31;
   const bool leader = (lane == (__ffs(grp) - 1));
   for (int k = 0; k < nbSamples; k++) {
     bool vote = false;
@@ -432,9 +600,14 @@ __global__ void tps_eval_samples_kernel(TpsArgs a, const float4* __restrict__ sa
   }
 }
 
-__global__ void tps_select_samples_kernel(TpsArgs a, float4* samples, const int* votes, int nbSamples) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.S) return;
+__global__ void tps_eval_samples_kernel(TpsArgs a, const float4* samples, int* votes, int nbSamples) {
+  // blockDim.x == 32: a warp is one 32-pixel row segment
+  tps_eval_row_item(a, samples, votes, nbSamples, blockIdx.x * blockDim.x + threadIdx.x,
+                    blockIdx.y * blockDim.y + threadIdx.y);
+}
+
+__device__ __forceinline__ void tps_select_item(const TpsArgs& a, float4* samples, const int* votes, int nbSamples,
+                                                int idx) {
   float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < nbSamples; k++) {
     float4 th = samples[(size_t)idx * nbSamples + k];
@@ -447,10 +620,12 @@ __global__ void tps_select_samples_kernel(TpsArgs a, float4* samples, const int*
   c->dx = c->dy = c->dxx = c->dyy = c->dxy = c->dn = c->dxd = c->dyd = c->dd = 0;
 }
 
-__global__ void tps_init_disp_kernel(TpsArgs a, int ransac) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= a.W || y >= a.H) return;
+__global__ void tps_select_samples_kernel(TpsArgs a, float4* samples, const int* votes, int nbSamples) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < a.S) tps_select_item(a, samples, votes, nbSamples, idx);
+}
+
+__device__ __forceinline__ void tps_init_disp_item(const TpsArgs& a, int ransac, int x, int y) {
   const size_t p = (size_t)y * a.W + x;
   const int index = a.labels[p];
   const float d = a.disp[p];
@@ -475,87 +650,275 @@ __global__ void tps_init_disp_kernel(TpsArgs a, int ransac) {
   a.inliers[p] = inlier;
 }
 
+__global__ void tps_init_disp_kernel(TpsArgs a, int ransac) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x < a.W && y < a.H) tps_init_disp_item(a, ransac, x, y);
+}
+
 // ---- plane smoothing (TPS_RGBD.cu:480-505; TPS_RGBD_kernels.cu:510-614) -----------
-// Single CTA, Jacobi (double buffered).  Node record: X.xyz, Z.xyz, px, py.
+// Jacobi (double buffered).  Node record: X.xyz, Z.xyz, px, py.
+__device__ __forceinline__ void tps_filter_init_item(const TpsArgs& a, float* buf, int i) {
+  const Superpixel s = a.sp[i];
+  const float X0 = s.xy_rg.x * s.theta_b.x + s.xy_rg.y * s.theta_b.y + s.theta_b.z;
+  float* n = buf + 8 * (size_t)i;
+  n[0] = X0; n[1] = s.theta_b.x; n[2] = s.theta_b.y;
+  n[3] = X0; n[4] = s.theta_b.x; n[5] = s.theta_b.y;
+  n[6] = s.xy_rg.x; n[7] = s.xy_rg.y;
+}
+
+__device__ __forceinline__ void tps_filter_iter_item(const TpsArgs& a, const float* cur, float* nxt, int idx,
+                                                     float alpha, float beta, float threshold) {
+  const int vv[4] = {-1, 0, 0, 1};
+  const int uu[4] = {0, -1, 1, 0};
+  const int x = idx % a.gx, y = idx / a.gx;
+  const float* ni = cur + 8 * (size_t)idx;
+  const V3 Xi = v3(ni[0], ni[1], ni[2]);
+  const V3 Zi = v3(ni[3], ni[4], ni[5]);
+  const float pxi = ni[6], pyi = ni[7];
+  Sym3 A = sym3(alpha, 0.f, 0.f, alpha, 0.f, alpha);
+  V3 R = alpha * Zi;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int yy = y + vv[j], xx = x + uu[j];
+    if (yy >= 0 && yy < a.gy && xx >= 0 && x < a.gx) {   // sic: x, not xx (reference :582-583)
+      const int nidx = yy * a.gx + xx;
+      if (nidx >= a.S) continue;
+      const float* nj = cur + 8 * (size_t)nidx;
+      const V3 Xj = v3(nj[0], nj[1], nj[2]);
+      const float dx = pxi - nj[6];
+      const float dy = pyi - nj[7];
+      const float dz = Xi.x - Xj.x;
+      if (isfinite(dz) && dz * dz < threshold * threshold) {
+        A.xx += beta * 2.f;
+        A.xy += -beta * dx;
+        A.xz += -beta * dy;
+        A.yy += beta * (2.f + dx * dx);
+        A.yz += beta * (dx * dy);
+        A.zz += beta * (2.f + dy * dy);
+        R.x += beta * (2.f * Xj.x + dx * Xj.y + dy * Xj.z);
+        R.y += beta * (-dx * Xj.x + 2.f * Xj.y);
+        R.z += beta * (-dy * Xj.x + 2.f * Xj.z);
+      }
+    }
+  }
+  float* no = nxt + 8 * (size_t)idx;
+  Sym3 Ai;
+  V3 Xn = Xi;
+  if (invert(A, Ai)) Xn = Ai * R;
+  no[0] = Xn.x; no[1] = Xn.y; no[2] = Xn.z;
+  no[3] = Zi.x; no[4] = Zi.y; no[5] = Zi.z; no[6] = pxi; no[7] = pyi;
+}
+
+__device__ __forceinline__ void tps_filter_finish_item(const TpsArgs& a, const float* cur, int i) {
+  const float* n = cur + 8 * (size_t)i;
+  Superpixel& s = a.sp[i];
+  const float X0 = n[0], X1 = n[1], X2 = n[2];
+  s.theta_b.x = X1;
+  s.theta_b.y = X2;
+  s.theta_b.z = X0 - s.xy_rg.x * X1 - s.xy_rg.y * X2;
+}
+
+// single-CTA version (multi-kernel path)
 __global__ void __launch_bounds__(1024) tps_filter_kernel(TpsArgs a, float* bufA, float* bufB, int iters, float alpha,
                                                           float beta, float threshold) {
-  const int S = a.S;
-  for (int i = threadIdx.x; i < S; i += blockDim.x) {
-    const Superpixel s = a.sp[i];
-    const float X0 = s.xy_rg.x * s.theta_b.x + s.xy_rg.y * s.theta_b.y + s.theta_b.z;
-    float* n = bufA + 8 * (size_t)i;
-    n[0] = X0; n[1] = s.theta_b.x; n[2] = s.theta_b.y;
-    n[3] = X0; n[4] = s.theta_b.x; n[5] = s.theta_b.y;
-    n[6] = s.xy_rg.x; n[7] = s.xy_rg.y;
-  }
+  for (int i = threadIdx.x; i < a.S; i += blockDim.x) tps_filter_init_item(a, bufA, i);
   __syncthreads();
   float* cur = bufA;
   float* nxt = bufB;
-  const int vv[4] = {-1, 0, 0, 1};
-  const int uu[4] = {0, -1, 1, 0};
   for (int it = 0; it < iters; it++) {
-    for (int idx = threadIdx.x; idx < S; idx += blockDim.x) {
-      const int x = idx % a.gx, y = idx / a.gx;
-      const float* ni = cur + 8 * (size_t)idx;
-      const V3 Xi = v3(ni[0], ni[1], ni[2]);
-      const V3 Zi = v3(ni[3], ni[4], ni[5]);
-      const float pxi = ni[6], pyi = ni[7];
-      Sym3 A = sym3(alpha, 0.f, 0.f, alpha, 0.f, alpha);
-      V3 R = alpha * Zi;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int yy = y + vv[j], xx = x + uu[j];
-        if (yy >= 0 && yy < a.gy && xx >= 0 && x < a.gx) {   // sic: x, not xx (reference :582-583)
-          const int nidx = yy * a.gx + xx;
-          if (nidx >= S) continue;
-          const float* nj = cur + 8 * (size_t)nidx;
-          const V3 Xj = v3(nj[0], nj[1], nj[2]);
-          const float dx = pxi - nj[6];
-          const float dy = pyi - nj[7];
-          const float dz = Xi.x - Xj.x;
-          if (isfinite(dz) && dz * dz < threshold * threshold) {
-            A.xx += beta * 2.f;
-            A.xy += -beta * dx;
-            A.xz += -beta * dy;
-            A.yy += beta * (2.f + dx * dx);
-            A.yz += beta * (dx * dy);
-            A.zz += beta * (2.f + dy * dy);
-            R.x += beta * (2.f * Xj.x + dx * Xj.y + dy * Xj.z);
-            R.y += beta * (-dx * Xj.x + 2.f * Xj.y);
-            R.z += beta * (-dy * Xj.x + 2.f * Xj.z);
-          }
-        }
-      }
-      float* no = nxt + 8 * (size_t)idx;
-      Sym3 Ai;
-      V3 Xn = Xi;
-      if (invert(A, Ai)) Xn = Ai * R;
-      no[0] = Xn.x; no[1] = Xn.y; no[2] = Xn.z;
-      no[3] = Zi.x; no[4] = Zi.y; no[5] = Zi.z; no[6] = pxi; no[7] = pyi;
-    }
+    for (int idx = threadIdx.x; idx < a.S; idx += blockDim.x) tps_filter_iter_item(a, cur, nxt, idx, alpha, beta, threshold);
     __syncthreads();
     float* t = cur; cur = nxt; nxt = t;
   }
-  for (int i = threadIdx.x; i < S; i += blockDim.x) {
-    const float* n = cur + 8 * (size_t)i;
-    Superpixel& s = a.sp[i];
-    const float X0 = n[0], X1 = n[1], X2 = n[2];
-    s.theta_b.x = X1;
-    s.theta_b.y = X2;
-    s.theta_b.z = X0 - s.xy_rg.x * X1 - s.xy_rg.y * X2;
-  }
+  for (int i = threadIdx.x; i < a.S; i += blockDim.x) tps_filter_finish_item(a, cur, i);
 }
 
 // ---- slanted-plane depth render (TPS_RGBD_kernels.cu:469-508) -> interleaved map -----
-__global__ void tps_render_kernel(TpsArgs a, int2* lmap) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= a.W || y >= a.H) return;
+__device__ __forceinline__ void tps_render_item(const TpsArgs& a, int2* lmap, int x, int y) {
   const size_t p = (size_t)y * a.W + x;
   const int index = a.labels[p];
   const float4 th = a.sp[index].theta_b;
   const float disp = (float)x * th.x + (float)y * th.y + th.z;
   lmap[p] = make_int2(index, __float_as_int(1.f / disp));
+}
+
+__global__ void tps_render_kernel(TpsArgs a, int2* lmap) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x < a.W && y < a.H) tps_render_item(a, lmap, x, y);
+}
+
+// ---- the whole segmentation as ONE persistent cooperative kernel ---------------------
+// 40 relabelling passes, 41 merges, RANSAC, smoothing and the render are phases of a
+// grid-stride kernel separated by grid-wide barriers (~1 us each) instead of ~90 dependent
+// kernel launches (~4-7 us each at VGA, where every phase is far too small to fill the
+// GPU).  One CTA per SM, co-resident by construction (cooperative launch).
+struct TpsRun {
+  int nb_iters, use_ransac, nb_samples, filter_iters;
+  float alpha, beta, threshold, radius;
+  float4* samples;
+  int* votes;
+  curandState* states;
+  float* filt_a;
+  float* filt_b;
+  int2* lmap;
+  unsigned int* barrier;
+  int cache_slots;       // capacity of the shared-memory superpixel cache
+  unsigned long long* trace;   // optional per-CTA phase timestamps (profiling aid), else NULL
+};
+
+constexpr int TPS_PERSIST_THREADS = 512;
+
+// Grid-wide barrier for the co-resident CTAs of the persistent kernel: one release
+// atomic per CTA on a monotonically increasing ticket and an acquire spin by thread 0
+// (cooperative_groups::grid_group::sync costs ~5 us here; this is ~1 us).  The acquire
+// at gpu scope also drops the SM's L1 lines, so the plain loads that follow observe
+// what the other CTAs wrote before their release.
+struct GridBarrier {
+  unsigned int* ticket;
+  unsigned int target;
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      target += gridDim.x;
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ticket) : "memory");
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ticket) : "memory");
+      } while ((int)(seen - target) < 0);
+    }
+    __syncthreads();
+  }
+};
+
+// One relabelling pass of the persistent kernel.  The CTA owns a band of active rows for
+// the whole kernel; it first rebuilds its shared-memory cache of superpixel means from the
+// (now quiescent) sums -- which replaces the separate merge phase and its barrier -- then
+// relabels its band, then meets the other CTAs at the barrier.
+__device__ __forceinline__ unsigned long long tps_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// trace layout: [cta][slot] with 4 stamps per pass (start, cache ready, items done, barrier passed)
+constexpr int TPS_TRACE_SLOTS = 512;
+struct TpsTrace {
+  unsigned long long* base;
+  int n;
+  __device__ __forceinline__ void stamp() {
+    if (base && threadIdx.x == 0 && n < TPS_TRACE_SLOTS) base[(size_t)blockIdx.x * TPS_TRACE_SLOTS + n++] = tps_now();
+  }
+};
+
+struct TpsBand {
+  int ry0, ry1;        // active-row range [ry0, ry1) of this CTA (row y = 2*ry + OY)
+  int first, count;    // cached superpixel ids
+};
+
+template <bool DISP>
+__device__ __forceinline__ void tps_phase_pass(const TpsArgs& a, GridBarrier& grid, Superpixel* cache,
+                                               const TpsBand& band, int OX, int OY, TpsTrace& tr) {
+  tr.stamp();
+  for (int i = threadIdx.x; i < band.count; i += blockDim.x)
+    cache[i] = tps_superpixel_from_sums<DISP>(a.sums[band.first + i]);
+  __syncthreads();
+  tr.stamp();
+  const SpCached<DISP> src = {cache, a.sums, band.first, band.count};
+  const int pairs = a.raw_w / 2 + 1;
+  const int items = 2 * pairs * (band.ry1 - band.ry0);     // one lane per pixel, partners adjacent
+  for (int base = 0; base < items; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int pr = i >> 1;
+    tps_pass_pixel<DISP>(a, src, pr % pairs, i & 1, band.ry0 + pr / pairs, OX, OY, i < items);
+  }
+  __syncthreads();
+  tr.stamp();
+  grid.sync();
+  tr.stamp();
+}
+
+__device__ __forceinline__ void tps_phase_merge_global(const TpsArgs& a, GridBarrier& grid, int tid, int nth, bool disp) {
+  for (int k = tid; k < a.S; k += nth) {
+    if (disp) tps_merge_item<true>(a, k);
+    else tps_merge_item<false>(a, k);
+  }
+  grid.sync();
+}
+
+__global__ void __launch_bounds__(TPS_PERSIST_THREADS, 1) tps_persistent_kernel(TpsArgs a, TpsRun r) {
+  GridBarrier grid;
+  grid.ticket = r.barrier;
+  grid.target = 0;   // the ticket is zeroed by a memset node ahead of this kernel
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nth = gridDim.x * blockDim.x;
+  const int npix = a.W * a.H;
+  // band of active rows owned by this CTA, and the grid-cell rows its cache covers
+  extern __shared__ Superpixel sp_cache[];
+  TpsTrace tr = {r.trace, 0};
+  TpsBand band;
+  {
+    const int per = (a.raw_h + gridDim.x - 1) / gridDim.x;
+    band.ry0 = min(a.raw_h, (int)blockIdx.x * per);
+    band.ry1 = min(a.raw_h, band.ry0 + per);
+    const int y0 = 2 * band.ry0, y1 = min(a.H - 1, 2 * band.ry1 + 1);
+    // A boundary moves at most one pixel per pass, so after all 4*nb_iters passes a pixel's
+    // label was seeded at most `margin` grid-cell rows away: the cache always hits.
+    const int margin = (4 * r.nb_iters + 1 + a.cell - 1) / a.cell;
+    const int c0 = max(0, y0 / a.cell - margin), c1 = min(a.gy - 1, y1 / a.cell + margin);
+    band.first = c0 * a.gx;
+    band.count = (band.ry1 > band.ry0) ? min(r.cache_slots, (c1 - c0 + 1) * a.gx) : 0;
+  }
+  // pass order per iteration: (0,0) (1,1) (0,1) (1,0) (TPS_RGBD.cu:190-272).  One copy of the
+  // pass body per phase (not eight): the kernel must stay inside the instruction cache.
+#pragma unroll 1
+  for (int k = 0; k < 4 * (r.nb_iters / 2); k++) {
+    const int s4 = k & 3;
+    tps_phase_pass<false>(a, grid, sp_cache, band, (s4 == 1 || s4 == 3) ? 1 : 0, (s4 == 1 || s4 == 2) ? 1 : 0, tr);
+  }
+  if (r.nb_iters / 2 > 0) tps_phase_merge_global(a, grid, tid, nth, false);   // RANSAC reads the global means
+  tr.stamp();
+  if (r.use_ransac) {
+    for (int i = tid; i < a.S * r.nb_samples; i += nth)
+      tps_init_sample_item(a, r.samples, r.votes, r.states, 10, r.radius, i / r.nb_samples, i);
+    grid.sync();
+    {
+      const int segs = (a.W + 31) / 32;
+      const int rows = segs * a.H;
+      const int lane = threadIdx.x & 31;
+      for (int w = tid >> 5; w < rows; w += nth >> 5)
+        tps_eval_row_item(a, r.samples, r.votes, r.nb_samples, (w % segs) * 32 + lane, w / segs);
+    }
+    grid.sync();
+    for (int i = tid; i < a.S; i += nth) tps_select_item(a, r.samples, r.votes, r.nb_samples, i);
+    grid.sync();
+  }
+  for (int p = tid; p < npix; p += nth) tps_init_disp_item(a, r.use_ransac, p % a.W, p / a.W);
+  grid.sync();
+  for (int k = tid; k < a.S; k += nth) tps_merge_item<true>(a, k);
+  grid.sync();
+  tr.stamp();
+#pragma unroll 1
+  for (int k = 0; k < 4 * (r.nb_iters - r.nb_iters / 2); k++) {
+    const int s4 = k & 3;
+    tps_phase_pass<true>(a, grid, sp_cache, band, (s4 == 1 || s4 == 3) ? 1 : 0, (s4 == 1 || s4 == 2) ? 1 : 0, tr);
+  }
+  if (r.nb_iters - r.nb_iters / 2 > 0) tps_phase_merge_global(a, grid, tid, nth, true);   // the filter reads the global means
+  // plane smoothing
+  for (int i = tid; i < a.S; i += nth) tps_filter_init_item(a, r.filt_a, i);
+  grid.sync();
+  float* cur = r.filt_a;
+  float* nxt = r.filt_b;
+  for (int it = 0; it < r.filter_iters; it++) {
+    for (int i = tid; i < a.S; i += nth) tps_filter_iter_item(a, cur, nxt, i, r.alpha, r.beta, r.threshold);
+    grid.sync();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  for (int i = tid; i < a.S; i += nth) tps_filter_finish_item(a, cur, i);
+  grid.sync();
+  tr.stamp();
+  for (int p = tid; p < npix; p += nth) tps_render_item(a, r.lmap, p % a.W, p / a.W);
+  tr.stamp();
 }
 
 // ------------------------------------------------------------------- launchers
@@ -568,6 +931,31 @@ void tps_init_rng(Engine* e) {
 }
 
 size_t tps_rng_state_bytes() { return sizeof(curandState); }
+size_t tps_trace_bytes(int grid) { return (size_t)grid * TPS_TRACE_SLOTS * sizeof(unsigned long long); }
+
+// co-resident CTAs available to the persistent kernel (0 = cooperative launch unsupported)
+int tps_persistent_grid(int device, int gx, int gy, int cell, int height, int nb_iters, int* cache_slots) {
+  int coop = 0, sms = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  *cache_slots = 0;
+  if (!coop) return 0;
+  // rows of grid cells a band of ceil(H/2/sms) active rows touches, plus two on each side
+  const int raw_h = 16 * ((height / 2 + 15) / 16);
+  const int per = (raw_h + sms - 1) / sms;
+  const int margin = (4 * nb_iters + 1 + cell - 1) / cell;
+  int rows = (2 * per + 1) / cell + 2 + 2 * margin;
+  if (rows > gy) rows = gy;
+  const int slots = rows * gx;
+  const int max_slots = (200 * 1024) / (int)sizeof(Superpixel);
+  if (slots > max_slots) return 0;   // image too large for the cached scheme: multi-kernel path
+  const size_t smem = (size_t)slots * sizeof(Superpixel);
+  cudaFuncSetAttribute(tps_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tps_persistent_kernel, TPS_PERSIST_THREADS, smem);
+  if (per_sm <= 0) return 0;
+  *cache_slots = slots;
+  return sms;
+}
 
 void launch_ingest(Engine* e, const uint8_t* rgb_dev, size_t rgb_stride, const float* depth_dev,
                    size_t depth_stride) {
@@ -588,6 +976,27 @@ static void launch_pass(Engine* e, const TpsArgs& a, int OX, int OY) {
 void launch_tps(Engine* e) {
   TpsArgs a = tps_args(e);
   const int nbIters = e->cfg.seg_iter;
+  if (e->tps_persistent) {
+    TpsRun r;
+    r.nb_iters = nbIters; r.use_ransac = e->cfg.seg_use_ransac; r.nb_samples = e->cfg.nb_samples;
+    r.filter_iters = e->cfg.filter_iter;
+    r.alpha = e->cfg.filter_alpha; r.beta = e->cfg.filter_beta; r.threshold = e->cfg.filter_threshold;
+    r.radius = (float)e->cfg.cell_size / 2.f;
+    r.samples = e->samples;
+    r.votes = reinterpret_cast<int*>(e->samples + (size_t)e->S * e->cfg.nb_samples);
+    r.states = reinterpret_cast<curandState*>(e->rng);
+    r.filt_a = e->filt_a; r.filt_b = e->filt_b; r.lmap = e->lmap;
+    r.barrier = e->tps_barrier;
+    r.cache_slots = e->tps_cache_slots;
+    r.trace = e->tps_trace;
+    cudaMemsetAsync(e->tps_barrier, 0, sizeof(unsigned int), e->stream);
+    void* params[] = {&a, &r};
+    cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tps_persistent_kernel), dim3(e->tps_grid),
+                                dim3(TPS_PERSIST_THREADS), params, (size_t)e->tps_cache_slots * sizeof(Superpixel),
+                                e->stream);
+    e->launches++;
+    return;
+  }
   for (int k = 0; k < nbIters / 2; k++) {
     launch_pass<false>(e, a, 0, 0);
     launch_pass<false>(e, a, 1, 1);
