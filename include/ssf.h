@@ -200,6 +200,19 @@ int ssf_icp_system_enqueue(SsfHandle h, const float R[9], const float t[3], int 
  * pose.  Returns R_rel/t_rel (identity/zero when invalid). */
 int ssf_icp(SsfHandle h, const float* R_init, const float* t_init, float out29[29], float R_rel[9],
             float t_rel[3], int* iters, int* valid);
+/* The same loop driven step by step, for tile-parallel registration of one large frame across
+ * GPUs: every rank holds the whole frame state and a copy of the model,
+ * builds the system over ITS slice of the visible prefix, the 29 floats are summed across
+ * ranks in rank order (see supersurfel_fusion_b200/multi.py), and every rank applies the
+ * identical Gauss-Newton step.  src_begin must be a multiple of 4.
+ *   ssf_icp_begin  : dense_registration.cu:262-299 (loop set-up)
+ *   ssf_icp_build  : one computeSymmetricICPSystem launch over [src_begin, src_begin+src_count)
+ *   ssf_icp_solve  : dense_registration.cu:326-391 with the given (reduced) system
+ *   ssf_icp_finish : dense_registration.cu:394-421 (+ supersurfel_fusion.cu:313-328 when apply_to_pose) */
+int ssf_icp_begin(SsfHandle h, const float* R_init, const float* t_init);
+int ssf_icp_build(SsfHandle h, int src_begin, int src_count, float out29[29]);
+int ssf_icp_solve(SsfHandle h, const float sys29[29], int* done);
+int ssf_icp_finish(SsfHandle h, int apply_to_pose, float R_rel[9], float t_rel[3], int* iters, int* valid);
 /* Model update block of processFrame (supersurfel_fusion.cu:351-483) at the
  * handle's current pose and stamp. */
 int ssf_fuse(SsfHandle h);

@@ -704,6 +704,57 @@ int ssf_icp(SsfHandle h, const float* R_init, const float* t_init, float out29[2
   return SSF_OK;
 }
 
+int ssf_icp_begin(SsfHandle h, const float* R_init, const float* t_init) {
+  H_CHECK(h);
+  if ((R_init == nullptr) != (t_init == nullptr)) return SSF_ERR_INVALID_ARG;
+  if (R_init) launch_icp_begin(e, R_init, t_init);
+  else launch_icp_begin_from_pose(e);
+  SSF_CUDA(e, cudaGetLastError());
+  return SSF_OK;
+}
+
+int ssf_icp_build(SsfHandle h, int src_begin, int src_count, float out29[29]) {
+  H_CHECK(h);
+  if (!out29 || src_begin < 0 || src_count < 0 || (src_begin & 3) || src_begin + src_count > e->cap)
+    return SSF_ERR_INVALID_ARG;
+  if (src_count > 0) launch_icp_build_range(e, src_begin, src_count);
+  else SSF_CUDA(e, cudaMemsetAsync(e->icp->sys, 0, sizeof(float) * 32, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(out29, e->icp->sys, 29 * sizeof(float), cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_CUDA(e, cudaGetLastError());
+  return SSF_OK;
+}
+
+int ssf_icp_solve(SsfHandle h, const float sys29[29], int* done) {
+  H_CHECK(h);
+  if (!sys29) return SSF_ERR_INVALID_ARG;
+  int rc = ensure_scratch(e, 256);
+  if (rc) return rc;
+  SSF_CUDA(e, cudaMemcpyAsync(e->scratch, sys29, 29 * sizeof(float), cudaMemcpyDefault, e->stream));
+  launch_icp_solve(e, reinterpret_cast<const float*>(e->scratch));
+  int d = 0;
+  SSF_CUDA(e, cudaMemcpyAsync(&d, &e->icp->done, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (done) *done = d;
+  return SSF_OK;
+}
+
+int ssf_icp_finish(SsfHandle h, int apply_to_pose, float R_rel[9], float t_rel[3], int* iters, int* valid) {
+  H_CHECK(h);
+  launch_icp_finish(e, apply_to_pose != 0);
+  IcpState* hs = nullptr;
+  SSF_CUDA(e, cudaMallocHost(reinterpret_cast<void**>(&hs), sizeof(IcpState)));
+  cudaError_t err = cudaMemcpyAsync(hs, e->icp, sizeof(IcpState), cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  if (err != cudaSuccess) { cudaFreeHost(hs); e->err = cudaGetErrorString(err); return SSF_ERR_CUDA; }
+  if (R_rel) memcpy(R_rel, hs->Rrel, 36);
+  if (t_rel) memcpy(t_rel, hs->trel, 12);
+  if (iters) *iters = hs->active ? hs->iter : 0;
+  if (valid) *valid = hs->active ? hs->valid : 0;
+  cudaFreeHost(hs);
+  return SSF_OK;
+}
+
 int ssf_fuse(SsfHandle h) {
   H_CHECK(h);
   launch_fuse(e);

@@ -141,6 +141,8 @@ void launch_icp_begin(Engine* e, const float* Rinit_or_null, const float* tinit_
 void launch_icp_begin_from_pose(Engine* e);
 void launch_icp_set_transform(Engine* e, const float* R, const float* t);
 void launch_icp_loop(Engine* e);
+void launch_icp_build_range(Engine* e, int begin, int count);
+void launch_icp_solve(Engine* e, const float* sys29_dev);
 void launch_icp_finish(Engine* e, bool apply_to_pose);
 void launch_ingest(Engine* e, const uint8_t* rgb_dev, size_t rgb_stride, const float* depth_dev,
                    size_t depth_stride);

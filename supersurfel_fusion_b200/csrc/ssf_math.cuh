@@ -191,4 +191,29 @@ __device__ __forceinline__ long long quantize(float v, double scale, double clam
   return __double2ll_rn(s);
 }
 
+// Warp-level pre-reduction of order-free integer sums keyed by a label: the lanes of a warp
+// (32 consecutive pixels of a row) are cut into runs of equal labels, every run is summed
+// with shuffles, and only the first lane of a run issues the atomics.  All 32 lanes must
+// call these; lanes with nothing to add pass zeros.
+__device__ __forceinline__ int run_head_lane(int label) {
+  const int lane = threadIdx.x & 31;
+  const int prev = __shfl_up_sync(0xffffffffu, label, 1);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != label);
+  return 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+}
+template <int N>
+__device__ __forceinline__ void run_reduce(long long (&v)[N], int head) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int oh = __shfl_down_sync(0xffffffffu, head, o);
+    const bool take = (lane + o < 32) && (oh == head);
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const long long vv = __shfl_down_sync(0xffffffffu, v[k], o);
+      if (take) v[k] += vv;
+    }
+  }
+}
+
 }  // namespace ssf

@@ -60,23 +60,36 @@ __device__ __forceinline__ V3 pose_t(const DevicePose* p) { return v3(p->t[0], p
 __global__ void extract_accumulate_kernel(const int2* __restrict__ lmap, const unsigned char* __restrict__ inliers,
                                           const int* __restrict__ bound, const uchar4* __restrict__ rgba,
                                           unsigned long long* __restrict__ xsums, CamK cam) {
+  // blockDim.x == 32: a warp is 32 consecutive pixels of one row
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= cam.W || y >= cam.H) return;
-  const size_t p = (size_t)y * cam.W + x;
-  if (!inliers[p]) return;
-  const int2 lz = lmap[p];
+  const bool in = (x < cam.W && y < cam.H);
+  const size_t p = in ? (size_t)y * cam.W + x : 0;
+  const int2 lz = in ? lmap[p] : make_int2(-1, 0);
   const float depth = __int_as_float(lz.y);
-  if (!(isfinite(depth) && depth > 0.0f && bound[p] == 0)) return;
-  const uchar4 c = rgba[p];
-  const V3 pos = v3(((float)x - cam.cx) * depth / cam.fx, ((float)y - cam.cy) * depth / cam.fy, depth);
-  const V3 lab = rgb_to_lab(v3((float)c.x, (float)c.y, (float)c.z));
-  const Sym3 o = outer(pos);
-  unsigned long long* a = xsums + (size_t)lz.x * 16;
-  const float vals[12] = {pos.x, pos.y, pos.z, lab.x, lab.y, lab.z, o.xx, o.xy, o.xz, o.yy, o.yz, o.zz};
+  const bool use = in && inliers[p] && isfinite(depth) && depth > 0.0f && bound[p] == 0;
+  long long v[13];
 #pragma unroll
-  for (int k = 0; k < 12; k++) atomicAdd(&a[k], (unsigned long long)quantize(vals[k], kFix, kFixClamp));
-  atomicAdd(&a[12], 1ull);
+  for (int k = 0; k < 13; k++) v[k] = 0;
+  if (use) {
+    const uchar4 c = rgba[p];
+    const V3 pos = v3(((float)x - cam.cx) * depth / cam.fx, ((float)y - cam.cy) * depth / cam.fy, depth);
+    const V3 lab = rgb_to_lab(v3((float)c.x, (float)c.y, (float)c.z));
+    const Sym3 o = outer(pos);
+    const float vals[12] = {pos.x, pos.y, pos.z, lab.x, lab.y, lab.z, o.xx, o.xy, o.xz, o.yy, o.yz, o.zz};
+#pragma unroll
+    for (int k = 0; k < 12; k++) v[k] = quantize(vals[k], kFix, kFixClamp);
+    v[12] = 1;
+  }
+  // one set of atomics per run of equal labels instead of one per pixel
+  const int head = run_head_lane(lz.x);
+  if (__ballot_sync(0xffffffffu, use) == 0u) return;
+  run_reduce<13>(v, head);
+  if ((int)(threadIdx.x & 31) == head && lz.x >= 0 && v[12] != 0) {
+    unsigned long long* a = xsums + (size_t)lz.x * 16;
+#pragma unroll
+    for (int k = 0; k < 13; k++) atomicAdd(&a[k], (unsigned long long)v[k]);
+  }
 }
 
 __device__ __forceinline__ float dequantize(unsigned long long v) {
@@ -490,8 +503,11 @@ __global__ void __launch_bounds__(PART_THREADS) partition_scatter_kernel(SurfelS
       int off = run[s];
       for (int w = 0; w < wid; w++) off += wcount[w][s];
       off += __popc(m[s] & ((1u << lane) - 1u));
-#pragma unroll 1
-      for (int p = 0; p < P_COUNT; p++) dst.plane(p)[off] = src.plane(p)[i];
+      float row[P_COUNT];
+#pragma unroll
+      for (int p = 0; p < P_COUNT; p++) row[p] = src.plane(p)[i];
+#pragma unroll
+      for (int p = 0; p < P_COUNT; p++) dst.plane(p)[off] = row[p];
     }
     __syncthreads();
     if (tid < 3) {
@@ -509,8 +525,11 @@ __global__ void partition_copyback_kernel(SurfelSet src, SurfelSet dst, const Co
   const int n = counters->pad;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-#pragma unroll 1
-  for (int p = 0; p < P_COUNT; p++) dst.plane(p)[i] = src.plane(p)[i];
+  float row[P_COUNT];
+#pragma unroll
+  for (int p = 0; p < P_COUNT; p++) row[p] = src.plane(p)[i];
+#pragma unroll
+  for (int p = 0; p < P_COUNT; p++) dst.plane(p)[i] = row[p];
 }
 
 __global__ void fuse_begin_kernel(Counters* counters) {

@@ -625,12 +625,17 @@ __global__ void tps_select_samples_kernel(TpsArgs a, float4* samples, const int*
   if (idx < a.S) tps_select_item(a, samples, votes, nbSamples, idx);
 }
 
-__device__ __forceinline__ void tps_init_disp_item(const TpsArgs& a, int ransac, int x, int y) {
-  const size_t p = (size_t)y * a.W + x;
-  const int index = a.labels[p];
-  const float d = a.disp[p];
+// All 32 lanes of a warp (32 consecutive pixels of a row) call this; `in` is false for lanes
+// beyond the image.  Moments are pre-reduced per run of equal labels.
+__device__ __forceinline__ void tps_init_disp_item(const TpsArgs& a, int ransac, int x, int y, bool in) {
+  const size_t p = in ? (size_t)y * a.W + x : 0;
+  const int index = in ? a.labels[p] : -1;
+  const float d = in ? a.disp[p] : 0.f;
   unsigned char inlier = 0;
-  if (isfinite(d)) {
+  long long v[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) v[k] = 0;
+  if (in && isfinite(d)) {
     bool okp = true;
     if (ransac) {
       const float4 th = a.sp[index].theta_b;
@@ -640,20 +645,26 @@ __device__ __forceinline__ void tps_init_disp_item(const TpsArgs& a, int ransac,
     }
     if (okp) {
       inlier = 0xff;
-      SpSums* s = &a.sums[index];
       const long long qd = quantize(d, kDispFix, kDispClamp);
-      add64(&s->dx, x); add64(&s->dy, y); add64(&s->dxx, (long long)x * x); add64(&s->dyy, (long long)y * y);
-      add64(&s->dxy, (long long)x * y); add64(&s->dxd, (long long)x * qd); add64(&s->dyd, (long long)y * qd);
-      add64(&s->dd, qd); add64(&s->dn, 1);
+      v[0] = x; v[1] = y; v[2] = (long long)x * x; v[3] = (long long)y * y; v[4] = (long long)x * y;
+      v[5] = (long long)x * qd; v[6] = (long long)y * qd; v[7] = qd; v[8] = 1;
     }
   }
-  a.inliers[p] = inlier;
+  if (in) a.inliers[p] = inlier;
+  const int head = run_head_lane(index);
+  if (__ballot_sync(0xffffffffu, inlier != 0) == 0u) return;
+  run_reduce<9>(v, head);
+  if ((int)(threadIdx.x & 31) == head && index >= 0 && v[8] != 0) {
+    SpSums* s = &a.sums[index];
+    add64(&s->dx, v[0]); add64(&s->dy, v[1]); add64(&s->dxx, v[2]); add64(&s->dyy, v[3]); add64(&s->dxy, v[4]);
+    add64(&s->dxd, v[5]); add64(&s->dyd, v[6]); add64(&s->dd, v[7]); add64(&s->dn, v[8]);
+  }
 }
 
 __global__ void tps_init_disp_kernel(TpsArgs a, int ransac) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x < a.W && y < a.H) tps_init_disp_item(a, ransac, x, y);
+  tps_init_disp_item(a, ransac, x, y, x < a.W && y < a.H);   // blockDim.x == 32
 }
 
 // ---- plane smoothing (TPS_RGBD.cu:480-505; TPS_RGBD_kernels.cu:510-614) -----------
@@ -893,7 +904,15 @@ __global__ void __launch_bounds__(TPS_PERSIST_THREADS, 1) tps_persistent_kernel(
     for (int i = tid; i < a.S; i += nth) tps_select_item(a, r.samples, r.votes, r.nb_samples, i);
     grid.sync();
   }
-  for (int p = tid; p < npix; p += nth) tps_init_disp_item(a, r.use_ransac, p % a.W, p / a.W);
+  {
+    const int segs = (a.W + 31) / 32;
+    const int rows = segs * a.H;
+    const int lane = threadIdx.x & 31;
+    for (int w = tid >> 5; w < rows; w += nth >> 5) {
+      const int x = (w % segs) * 32 + lane;
+      tps_init_disp_item(a, r.use_ransac, x, w / segs, x < a.W);
+    }
+  }
   grid.sync();
   for (int k = tid; k < a.S; k += nth) tps_merge_item<true>(a, k);
   grid.sync();
@@ -967,6 +986,8 @@ void launch_ingest(Engine* e, const uint8_t* rgb_dev, size_t rgb_stride, const f
 template <bool DISP>
 static void launch_pass(Engine* e, const TpsArgs& a, int OX, int OY) {
   const int pairs = a.raw_w / 2 + 1;
+  // (fusing the merge into the pass as "last CTA done" was measured 40 % slower per frame: one
+  // CTA merging 1200 superpixels serialises five dependent L2 round trips)
   dim3 blk(32, 4), grd(cdiv(pairs, 32), cdiv(a.raw_h, 4));
   tps_pass_kernel<DISP><<<grd, blk, 0, e->stream>>>(a, OX, OY);
   tps_merge_kernel<DISP><<<cdiv(a.S, 128), 128, 0, e->stream>>>(a);

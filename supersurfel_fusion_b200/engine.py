@@ -66,7 +66,8 @@ EXPORTS = [
     "ssf_copy_frame", "ssf_get_segmentation", "ssf_render_preview", "ssf_get_slanted_depth", "ssf_export_model",
     "ssf_extract_local_point_cloud", "ssf_invalidate_frame_supersurfels", "ssf_transform_model", "ssf_set_model",
     "ssf_set_frame", "ssf_set_segmentation", "ssf_tps_segment", "ssf_get_ransac_samples",
-    "ssf_generate_supersurfels", "ssf_icp_system", "ssf_icp_system_enqueue", "ssf_icp", "ssf_fuse",
+    "ssf_generate_supersurfels", "ssf_icp_system", "ssf_icp_system_enqueue", "ssf_icp", "ssf_icp_begin",
+    "ssf_icp_build", "ssf_icp_solve", "ssf_icp_finish", "ssf_fuse",
     "ssf_timer_start", "ssf_timer_stop", "ssf_synchronize", "ssf_get_launch_count",
 ]
 
@@ -404,6 +405,33 @@ class SupersurfelFusion:
                                C.byref(valid))
         self._check(rc, "ssf_icp")
         return bool(valid.value), R.reshape(3, 3), t, dict(iters=iters.value, valid=valid.value, system=sys29)
+
+    # -- step-wise loop for tile-parallel registration (see multi.py) ---------------------------
+    def icpBegin(self, R_init=None, t_init=None):
+        Ri = None if R_init is None else np.ascontiguousarray(R_init, np.float32).reshape(9)
+        ti = None if t_init is None else np.ascontiguousarray(t_init, np.float32).reshape(3)
+        self._check(self._lib.ssf_icp_begin(self._h, _ptr(Ri), _ptr(ti)), "ssf_icp_begin")
+
+    def icpBuild(self, src_begin, src_count):
+        out = np.zeros(29, np.float32)
+        self._check(self._lib.ssf_icp_build(self._h, C.c_int(src_begin), C.c_int(src_count), _ptr(out)),
+                    "ssf_icp_build")
+        return out
+
+    def icpSolve(self, sys29):
+        sys29 = np.ascontiguousarray(sys29, np.float32).reshape(29)
+        done = C.c_int()
+        self._check(self._lib.ssf_icp_solve(self._h, _ptr(sys29), C.byref(done)), "ssf_icp_solve")
+        return bool(done.value)
+
+    def icpFinish(self, apply_to_pose=False):
+        R = np.zeros(9, np.float32)
+        t = np.zeros(3, np.float32)
+        iters, valid = C.c_int(), C.c_int()
+        rc = self._lib.ssf_icp_finish(self._h, C.c_int(int(apply_to_pose)), _ptr(R), _ptr(t), C.byref(iters),
+                                      C.byref(valid))
+        self._check(rc, "ssf_icp_finish")
+        return bool(valid.value), R.reshape(3, 3), t, dict(iters=iters.value, valid=valid.value)
 
     def fuse(self):
         self._check(self._lib.ssf_fuse(self._h), "ssf_fuse")
