@@ -213,6 +213,19 @@ int ssf_icp_begin(SsfHandle h, const float* R_init, const float* t_init);
 int ssf_icp_build(SsfHandle h, int src_begin, int src_count, float out29[29]);
 int ssf_icp_solve(SsfHandle h, const float sys29[29], int* done);
 int ssf_icp_finish(SsfHandle h, int apply_to_pose, float R_rel[9], float t_rel[3], int* iters, int* valid);
+/* Fused build + exchange + solve over NVLink peer memory (no NCCL, no host round trip per
+ * iteration): every rank's system kernel stores its 29 partial sums straight into every
+ * peer's exchange buffer (P2P stores over NVLink), waits for the peers' flags, sums the
+ * slices in rank order and runs the Gauss-Newton step -- so all ranks iterate in lock step
+ * inside their own kernels.  Set-up: exchange ssf_peer_handle() blobs between the ranks
+ * (any transport; bench/tests use torch.distributed.all_gather) and call ssf_connect_peers()
+ * once.  ssf_icp_tiled() is collective: every rank must call it with the same R_init/t_init. */
+#define SSF_PEER_HANDLE_BYTES 64
+#define SSF_MAX_PEERS 8
+int ssf_peer_handle(SsfHandle h, void* handle64);
+int ssf_connect_peers(SsfHandle h, int rank, int world, const void* handles);
+int ssf_icp_tiled(SsfHandle h, const float* R_init, const float* t_init, int src_begin, int src_count,
+                  float out29[29], float R_rel[9], float t_rel[3], int* iters, int* valid);
 /* Model update block of processFrame (supersurfel_fusion.cu:351-483) at the
  * handle's current pose and stamp. */
 int ssf_fuse(SsfHandle h);

@@ -242,10 +242,13 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   A(dalloc(&e->states, (size_t)e->cap));
   A(dalloc(&e->scan_tmp, (size_t)8 + 4 * ((size_t)(e->cap + 1023) / 1024)));
   A(dalloc(&e->icp, (size_t)1)); A(dalloc(&e->icp_partials, (size_t)e->icp_grid * 32));
+  A(dalloc(&e->xbuf, (size_t)2 * SSF_MAX_PEERS * 64)); A(dalloc(&e->xpeers_dev, (size_t)SSF_MAX_PEERS));
+  e->xrank = 0; e->xworld = 1;
   A(dalloc(&e->counters, (size_t)1)); A(dalloc(&e->pose, (size_t)1));
   A(dalloc(&e->d_report, (size_t)1));
   A(cudaMallocHost(reinterpret_cast<void**>(&e->h_report), sizeof(FrameReport)));
   A(cudaMallocHost(reinterpret_cast<void**>(&e->h_prior), 12 * sizeof(float)));
+  A(cudaMallocHost(reinterpret_cast<void**>(&e->h_icp), sizeof(IcpState)));
 #undef A
   if (err != cudaSuccess) {
     fprintf(stderr, "ssf_create: %s\n", cudaGetErrorString(err));
@@ -270,14 +273,17 @@ int ssf_destroy(SsfHandle h) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   if (e->graph_ready) cudaGraphExecDestroy(e->graph_exec);
+  for (int g = 0; g < SSF_MAX_PEERS; g++)
+    if (e->xpeer_open[g]) cudaIpcCloseMemHandle(e->xpeer_open[g]);
   void* bufs[] = {e->rgba, e->disp, e->labels, e->bound, e->inliers, e->lmap, e->in_rgb, e->in_depth, e->sp, e->sums,
-                  e->samples, e->rng, e->filt_a, e->filt_b, e->xsums, e->tps_barrier, e->tps_trace, e->frame.base, e->model.base,
+                  e->samples, e->rng, e->filt_a, e->filt_b, e->xsums, e->tps_barrier, e->tps_trace, e->xbuf, e->xpeers_dev, e->frame.base, e->model.base,
                   e->model_alt.base, e->ftab, e->matched, e->best, e->states, e->scan_tmp, e->icp, e->icp_partials,
                   e->counters, e->pose, e->d_report, e->scratch};
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (e->h_report) cudaFreeHost(e->h_report);
   if (e->h_prior) cudaFreeHost(e->h_prior);
+  if (e->h_icp) cudaFreeHost(e->h_icp);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->evf0) cudaEventDestroy(e->evf0);
@@ -690,17 +696,14 @@ int ssf_icp(SsfHandle h, const float* R_init, const float* t_init, float out29[2
   else launch_icp_begin_from_pose(e);
   launch_icp_loop(e);
   launch_icp_finish(e, false);
-  IcpState* hs = nullptr;
-  SSF_CUDA(e, cudaMallocHost(reinterpret_cast<void**>(&hs), sizeof(IcpState)));
-  cudaError_t err = cudaMemcpyAsync(hs, e->icp, sizeof(IcpState), cudaMemcpyDeviceToHost, e->stream);
-  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-  if (err != cudaSuccess) { cudaFreeHost(hs); e->err = cudaGetErrorString(err); return SSF_ERR_CUDA; }
+  IcpState* hs = e->h_icp;
+  SSF_CUDA(e, cudaMemcpyAsync(hs, e->icp, sizeof(IcpState), cudaMemcpyDeviceToHost, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   if (out29) memcpy(out29, hs->sys, 29 * sizeof(float));
   if (R_rel) memcpy(R_rel, hs->Rrel, 36);
   if (t_rel) memcpy(t_rel, hs->trel, 12);
   if (iters) *iters = hs->active ? hs->iter : 0;
   if (valid) *valid = hs->active ? hs->valid : 0;
-  cudaFreeHost(hs);
   return SSF_OK;
 }
 
@@ -742,16 +745,66 @@ int ssf_icp_solve(SsfHandle h, const float sys29[29], int* done) {
 int ssf_icp_finish(SsfHandle h, int apply_to_pose, float R_rel[9], float t_rel[3], int* iters, int* valid) {
   H_CHECK(h);
   launch_icp_finish(e, apply_to_pose != 0);
-  IcpState* hs = nullptr;
-  SSF_CUDA(e, cudaMallocHost(reinterpret_cast<void**>(&hs), sizeof(IcpState)));
-  cudaError_t err = cudaMemcpyAsync(hs, e->icp, sizeof(IcpState), cudaMemcpyDeviceToHost, e->stream);
-  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-  if (err != cudaSuccess) { cudaFreeHost(hs); e->err = cudaGetErrorString(err); return SSF_ERR_CUDA; }
+  IcpState* hs = e->h_icp;
+  SSF_CUDA(e, cudaMemcpyAsync(hs, e->icp, sizeof(IcpState), cudaMemcpyDeviceToHost, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   if (R_rel) memcpy(R_rel, hs->Rrel, 36);
   if (t_rel) memcpy(t_rel, hs->trel, 12);
   if (iters) *iters = hs->active ? hs->iter : 0;
   if (valid) *valid = hs->active ? hs->valid : 0;
-  cudaFreeHost(hs);
+  return SSF_OK;
+}
+
+int ssf_peer_handle(SsfHandle h, void* handle64) {
+  H_CHECK(h);
+  if (!handle64) return SSF_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == SSF_PEER_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  SSF_CUDA(e, cudaIpcGetMemHandle(&hd, e->xbuf));
+  memcpy(handle64, &hd, sizeof(hd));
+  return SSF_OK;
+}
+
+int ssf_connect_peers(SsfHandle h, int rank, int world, const void* handles) {
+  H_CHECK(h);
+  if (!handles || world < 1 || world > SSF_MAX_PEERS || rank < 0 || rank >= world) return SSF_ERR_INVALID_ARG;
+  float* ptrs[SSF_MAX_PEERS] = {nullptr};
+  for (int g = 0; g < world; g++) {
+    if (g == rank) { ptrs[g] = e->xbuf; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, static_cast<const char*>(handles) + (size_t)g * SSF_PEER_HANDLE_BYTES, sizeof(hd));
+    void* p = nullptr;
+    SSF_CUDA(e, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    e->xpeer_open[g] = p;
+    ptrs[g] = static_cast<float*>(p);
+  }
+  SSF_CUDA(e, cudaMemcpy(e->xpeers_dev, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice));
+  SSF_CUDA(e, cudaMemset(e->xbuf, 0, sizeof(float) * 2 * SSF_MAX_PEERS * 64));
+  unsigned int zero = 0;
+  SSF_CUDA(e, cudaMemcpy(&e->icp->xseq, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+  e->xrank = rank;
+  e->xworld = world;
+  return SSF_OK;
+}
+
+int ssf_icp_tiled(SsfHandle h, const float* R_init, const float* t_init, int src_begin, int src_count,
+                  float out29[29], float R_rel[9], float t_rel[3], int* iters, int* valid) {
+  H_CHECK(h);
+  if ((R_init == nullptr) != (t_init == nullptr)) return SSF_ERR_INVALID_ARG;
+  if (src_begin < 0 || src_count < 0 || (src_begin & 3) || src_begin + src_count > e->cap) return SSF_ERR_INVALID_ARG;
+  if (e->xworld < 2) return SSF_ERR_STATE;
+  if (R_init) launch_icp_begin(e, R_init, t_init);
+  else launch_icp_begin_from_pose(e);
+  launch_icp_tiled_loop(e, src_begin, src_count);
+  launch_icp_finish(e, false);
+  IcpState* hs = e->h_icp;
+  SSF_CUDA(e, cudaMemcpyAsync(hs, e->icp, sizeof(IcpState), cudaMemcpyDeviceToHost, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (out29) memcpy(out29, hs->sys, 29 * sizeof(float));
+  if (R_rel) memcpy(R_rel, hs->Rrel, 36);
+  if (t_rel) memcpy(t_rel, hs->trel, 12);
+  if (iters) *iters = hs->active ? hs->iter : 0;
+  if (valid) *valid = hs->active ? hs->valid : 0;
   return SSF_OK;
 }
 

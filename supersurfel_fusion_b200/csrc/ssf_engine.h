@@ -61,6 +61,7 @@ struct IcpState {
   int valid;
   int active;            // 0 when there is nothing to register against (bootstrap)
   unsigned int ticket;   // last-block-done counter
+  unsigned int xseq;     // sequence number of the cross-GPU exchange (never reset)
 };
 
 struct Counters {
@@ -122,6 +123,11 @@ struct Engine {
   int icp_grid;
   int icp_occ;           // resident CTAs per SM the system kernel is compiled for
   int icp_debug;         // profiling knob, see IcpArgs::debug
+  // tile-parallel registration over peer memory
+  float* xbuf;           // this rank's exchange buffer: [2 parities][SSF_MAX_PEERS][64 floats]
+  float** xpeers_dev;    // device array: exchange buffer of every rank (own entry = xbuf)
+  void* xpeer_open[SSF_MAX_PEERS];   // IPC mappings to close
+  int xrank, xworld;
 
   Counters* counters;
   DevicePose* pose;
@@ -143,6 +149,7 @@ void launch_icp_set_transform(Engine* e, const float* R, const float* t);
 void launch_icp_loop(Engine* e);
 void launch_icp_build_range(Engine* e, int begin, int count);
 void launch_icp_solve(Engine* e, const float* sys29_dev);
+void launch_icp_tiled_loop(Engine* e, int begin, int count);
 void launch_icp_finish(Engine* e, bool apply_to_pose);
 void launch_ingest(Engine* e, const uint8_t* rgb_dev, size_t rgb_stride, const float* depth_dev,
                    size_t depth_stride);

@@ -67,7 +67,8 @@ EXPORTS = [
     "ssf_extract_local_point_cloud", "ssf_invalidate_frame_supersurfels", "ssf_transform_model", "ssf_set_model",
     "ssf_set_frame", "ssf_set_segmentation", "ssf_tps_segment", "ssf_get_ransac_samples",
     "ssf_generate_supersurfels", "ssf_icp_system", "ssf_icp_system_enqueue", "ssf_icp", "ssf_icp_begin",
-    "ssf_icp_build", "ssf_icp_solve", "ssf_icp_finish", "ssf_fuse",
+    "ssf_icp_build", "ssf_icp_solve", "ssf_icp_finish", "ssf_peer_handle", "ssf_connect_peers", "ssf_icp_tiled",
+    "ssf_fuse",
     "ssf_timer_start", "ssf_timer_stop", "ssf_synchronize", "ssf_get_launch_count",
 ]
 
@@ -432,6 +433,30 @@ class SupersurfelFusion:
                                       C.byref(valid))
         self._check(rc, "ssf_icp_finish")
         return bool(valid.value), R.reshape(3, 3), t, dict(iters=iters.value, valid=valid.value)
+
+    # -- fused build + exchange + solve over NVLink peer memory ------------------------------
+    def peerHandle(self):
+        buf = np.zeros(64, np.uint8)
+        self._check(self._lib.ssf_peer_handle(self._h, _ptr(buf)), "ssf_peer_handle")
+        return buf
+
+    def connectPeers(self, rank, world, handles):
+        handles = np.ascontiguousarray(handles, np.uint8).reshape(world * 64)
+        self._check(self._lib.ssf_connect_peers(self._h, C.c_int(rank), C.c_int(world), _ptr(handles)),
+                    "ssf_connect_peers")
+
+    def icpTiled(self, src_begin, src_count, R_init=None, t_init=None):
+        """Collective: every rank calls it with the same R_init / t_init and its own slice."""
+        Ri = None if R_init is None else np.ascontiguousarray(R_init, np.float32).reshape(9)
+        ti = None if t_init is None else np.ascontiguousarray(t_init, np.float32).reshape(3)
+        sys29 = np.zeros(29, np.float32)
+        R = np.zeros(9, np.float32)
+        t = np.zeros(3, np.float32)
+        iters, valid = C.c_int(), C.c_int()
+        rc = self._lib.ssf_icp_tiled(self._h, _ptr(Ri), _ptr(ti), C.c_int(src_begin), C.c_int(src_count), _ptr(sys29),
+                                     _ptr(R), _ptr(t), C.byref(iters), C.byref(valid))
+        self._check(rc, "ssf_icp_tiled")
+        return bool(valid.value), R.reshape(3, 3), t, dict(iters=iters.value, valid=valid.value, system=sys29)
 
     def fuse(self):
         self._check(self._lib.ssf_fuse(self._h), "ssf_fuse")

@@ -81,3 +81,26 @@ def tile_parallel_icp(engine, dist, n_visible, R_init=None, t_init=None, device=
     valid, R, t, info = engine.icpFinish(apply_to_pose)
     info = dict(info, builds=builds, system=last, shard=(begin, count))
     return valid, R, t, info
+
+
+def connect_peers(engine, dist, device=None):
+    """Exchange the engines' peer-memory handles over `dist` and map every rank's exchange buffer
+    (once, after creating the engine).  Needed for fused_tile_parallel_icp()."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = torch.from_numpy(engine.peerHandle().copy())
+    if device is not None:
+        mine = mine.to(device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    handles = np.concatenate([p.cpu().numpy() for p in parts])
+    engine.connectPeers(rank, world, handles)
+
+
+def fused_tile_parallel_icp(engine, dist, n_visible, R_init=None, t_init=None):
+    """Same result as tile_parallel_icp(), but the slices' sums travel GPU-to-GPU by peer stores
+    inside the system kernel and every rank solves on the device: no NCCL call and no host round
+    trip per iteration (ssf_icp_tiled)."""
+    begin, count = shard_range(n_visible, dist.get_rank(), dist.get_world_size())
+    valid, R, t, info = engine.icpTiled(begin, count, R_init, t_init)
+    return valid, R, t, dict(info, shard=(begin, count))

@@ -1,0 +1,45 @@
+"""Multi-GPU tests (need >= 2 visible GPUs; skipped on a single-GPU box): tile-parallel ICP over
+NCCL against the single-GPU loop, and bench.py with two independent sequences."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _torchrun(n, script, *args, port=29533):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), script] + list(args)
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    return json.loads(lines[-1])
+
+
+def test_tile_parallel_icp_two_gpus():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun(2, "tools/tile_icp_check.py", str(1 << 20))
+    assert r["valid_single"] and r["valid_tiled"]
+    assert r["iters_single"] == r["iters_tiled"]
+    assert r["inliers_single"] == r["inliers_tiled"]
+    assert r["sys_rel"] < 1e-5 and r["dt"] < 1e-5 and r["dR"] < 1e-5     # north_star: pose within 1e-4 m
+    # the fused peer-memory loop (no NCCL, no host round trip) gives the same pose
+    assert r["valid_fused"] and r["iters_fused"] == r["iters_single"]
+    assert r["dt_fused"] < 1e-5 and r["dR_fused"] < 1e-5
+
+
+def test_bench_two_independent_sequences():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "60", "--warmup", "5", "--skip-extras", port=29534)
+    assert r["n_gpus"] == 2 and r["scaling"] == "weak" and r["value"] > 0 and r["gpu_launches"] > 0
