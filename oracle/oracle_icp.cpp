@@ -20,6 +20,14 @@ inline Mat33 ldm(const float* p) {
   return mkmat(mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5]), mk3(p[6], p[7], p[8]));
 }
 
+// Sum of three products as the fused chain fma(a.z, b.z, fma(a.y, b.y, a.x * b.x)): the
+// contraction nvcc applies to the reference's dot products (its SASS for
+// computeSymmetricICPSystem / makeCorrespondences reads FMUL, FFMA, FFMA, FADD for
+// R * p + t), fixed here so that the CUDA path (csrc/ssf_icp.cu, packed FFMA2 chains) and
+// this restatement take every gate decision on bit-identical numbers.
+inline float dotf(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+inline f3 mulf(const Mat33& m, f3 v) { return mk3(dotf(m.rows[0], v), dotf(m.rows[1], v), dotf(m.rows[2], v)); }
+
 // Per-source term of dense_registration_kernels.cuh:207-281.  Returns false when the
 // element contributes nothing; otherwise fills term[29].
 inline bool icp_term(int i, const float* src_pos, const float* src_col, const float* src_orient,
@@ -27,24 +35,29 @@ inline bool icp_term(int i, const float* src_pos, const float* src_col, const fl
                      const Mat33& R, f3 t, const OrcCam& cam, const int32_t* labels,
                      const float* depth, float* term) {
   f3 ps = ld3(src_pos, i);
-  ps = R * ps + t;
+  ps = mulf(R, ps) + t;
   int u = project_round(ps.x * cam.fx / ps.z + cam.cx);
   int v = project_round(ps.y * cam.fy / ps.z + cam.cy);
   if (!(u >= 0 && u < cam.width && v >= 0 && v < cam.height)) return false;
   int target_id = labels[v * cam.width + u];
   float zt = depth[v * cam.width + u];
   if (!(tgt_conf[target_id] > 0.0f && zt >= 0.2f && zt <= 5.0f)) return false;
-  float dist_color = length(rgbToLab(ld3(src_col, i)) - rgbToLab(ld3(tgt_col, target_id)));
+  f3 dl = rgbToLab(ld3(src_col, i)) - rgbToLab(ld3(tgt_col, target_id));
+  float dist_color = sqrtf(dotf(dl, dl));
   f3 pt = mk3(zt * ((float)u - cam.cx) / cam.fx, zt * ((float)v - cam.cy) / cam.fy, zt);
   f3 nt = mk3(tgt_orient[9 * target_id + 6], tgt_orient[9 * target_id + 7], tgt_orient[9 * target_id + 8]);
-  f3 ns = normalize(R * mk3(src_orient[9 * i + 6], src_orient[9 * i + 7], src_orient[9 * i + 8]));
-  if (!(dist_color < 20.0f && length(ps - pt) < 0.1f && fabsf(dot(nt, ns)) > 0.8f)) return false;
+  // normalize (vector_math.cuh:247-252): v * rsqrtf(v.v); the host has no rsqrtf, the
+  // correctly rounded 1/sqrt stands in (the device intrinsic is within 2 ulp of it)
+  f3 m = mulf(R, mk3(src_orient[9 * i + 6], src_orient[9 * i + 7], src_orient[9 * i + 8]));
+  f3 ns = m * (1.0f / sqrtf(dotf(m, m)));
+  f3 dd = ps - pt;
+  if (!(dist_color < 20.0f && sqrtf(dotf(dd, dd)) < 0.1f && fabsf(dotf(nt, ns)) > 0.8f)) return false;
   const float w = 1.0f;
   f3 d = pt - ps;
-  f3 c1 = cross(pt, ns);
-  f3 c2 = cross(ps, nt);
-  float dn1 = dot(d, ns);
-  float dn2 = dot(d, nt);
+  f3 c1 = mk3(fmaf(pt.y, ns.z, -(pt.z * ns.y)), fmaf(pt.z, ns.x, -(pt.x * ns.z)), fmaf(pt.x, ns.y, -(pt.y * ns.x)));
+  f3 c2 = mk3(fmaf(ps.y, nt.z, -(ps.z * nt.y)), fmaf(ps.z, nt.x, -(ps.x * nt.z)), fmaf(ps.x, nt.y, -(ps.y * nt.x)));
+  float dn1 = dotf(d, ns);
+  float dn2 = dotf(d, nt);
   float x1[6] = {c1.x, c1.y, c1.z, ns.x, ns.y, ns.z};
   float x2[6] = {c2.x, c2.y, c2.z, nt.x, nt.y, nt.z};
   int k = 0;

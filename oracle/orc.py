@@ -14,8 +14,13 @@ LIB_PATH = os.path.join(HERE, "liboracle.so")
 
 
 def build(force=False):
-    if force or not os.path.exists(LIB_PATH):
+    # make decides staleness (sources newer than the library); a box without the toolchain
+    # but with a prebuilt library (the GPU box always has both) just uses it
+    try:
         subprocess.check_call(["make", "-s", "-C", HERE, "-j8"] + (["-B"] if force else []))
+    except (OSError, subprocess.CalledProcessError):
+        if not os.path.exists(LIB_PATH):
+            raise
     return LIB_PATH
 
 

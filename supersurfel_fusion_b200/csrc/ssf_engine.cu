@@ -192,10 +192,13 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   const int sms = prop.multiProcessorCount;
-  const int need_blocks = (e->cap + 1023) / 1024;
-  e->icp_occ = 2;
-  if (const char* v = getenv("SSF_ICP_OCC")) e->icp_occ = atoi(v);   // tuning knob: 2, 3 or 4
-  if (e->icp_occ < 2 || e->icp_occ > 4) e->icp_occ = 2;
+  const int need_blocks = (e->cap + icp_chunk_size() - 1) / icp_chunk_size();
+  e->icp_occ = 3;
+  if (const char* v = getenv("SSF_ICP_OCC")) e->icp_occ = atoi(v);   // tuning knob: 3, 4 or 5
+  if (e->icp_occ < 3 || e->icp_occ > 5) e->icp_occ = 3;
+  e->icp_stages = 1;
+  if (const char* v = getenv("SSF_ICP_STAGES")) e->icp_stages = atoi(v);   // tuning knob: 1 (no ring) .. 4
+  e->icp_stages = icp_configure(e->icp_stages);
   e->tps_grid = tps_persistent_grid(device, e->gx, e->gy, cfg->cell_size, e->H, cfg->seg_iter, &e->tps_cache_slots);
   // The one-kernel (cooperative, band-owned) form of the segmentation is kept as an option:
   // measured on B200 at VGA it is ~8 % slower per frame than the graph of small kernels

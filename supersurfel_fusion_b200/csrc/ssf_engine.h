@@ -122,6 +122,7 @@ struct Engine {
   float* icp_partials;   // [grid][32]
   int icp_grid;
   int icp_occ;           // resident CTAs per SM the system kernel is compiled for
+  int icp_stages;        // depth of its TMA-fed shared-memory ring (SSF_ICP_STAGES, default 3)
   int icp_debug;         // profiling knob, see IcpArgs::debug
   // tile-parallel registration over peer memory
   float* xbuf;           // this rank's exchange buffer: [2 parities][SSF_MAX_PEERS][64 floats]
@@ -142,6 +143,9 @@ struct Engine {
 };
 
 // ---- stage launchers (each enqueues on e->stream, no host sync) -----------------
+int icp_chunk_size();     // supersurfels one CTA of the system kernel consumes per grid-stride step
+int icp_ctas_per_sm();
+int icp_configure(int stages);   // opts the system kernel in to its shared-memory ring; returns the clamped depth    // resident CTAs per SM the system kernel is compiled for
 void launch_icp_system(Engine* e, const SurfelSet& src, const int* n_dev, int n_host, bool solve);
 void launch_icp_begin(Engine* e, const float* Rinit_or_null, const float* tinit_or_null);  // host ptrs
 void launch_icp_begin_from_pose(Engine* e);

@@ -168,12 +168,17 @@ def test_icp_starved_is_invalid(orc, warm_state):
     assert np.array_equal(R, np.eye(3, dtype=np.float32)) and not t.any()
 
 
-def test_icp_large_problem_matches_oracle(orc):
-    """Streaming regime: more source supersurfels than one wave of CTAs (grid-stride path)."""
+@pytest.mark.parametrize("n_src,stages,occ", [(600000, "1", "3"), (600003, "1", "3"), (600000, "3", "3"),
+                                              (600001, "2", "4"), (600000, "1", "5")])
+def test_icp_large_problem_matches_oracle(orc, monkeypatch, n_src, stages, occ):
+    """Streaming regime: more source supersurfels than one wave of CTAs (grid-stride path), ragged
+    slice ends, and every tuning variant of the system kernel (TMA ring depth, register budget)."""
     from supersurfel_fusion_b200 import CamParam, SupersurfelFusion
-    prob = synthetic_icp_problem(600000, width=1280, height=960, seed=5)
+    monkeypatch.setenv("SSF_ICP_STAGES", stages)
+    monkeypatch.setenv("SSF_ICP_OCC", occ)
+    prob = synthetic_icp_problem(n_src, width=1280, height=960, seed=5)
     S = prob["S"]
-    eng = SupersurfelFusion().initialize(CamParam(*prob["cam"]), nb_supersurfels_max=600000)
+    eng = SupersurfelFusion().initialize(CamParam(*prob["cam"]), nb_supersurfels_max=n_src)
     assert eng.nbSuperpixels == S
     frame = Supersurfels(S)
     frame.colors[:] = prob["tgt_col"]; frame.orientations[:] = prob["tgt_ori"]; frame.confidences[:] = prob["tgt_conf"]

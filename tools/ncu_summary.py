@@ -2,7 +2,7 @@
 """Turn ncu outputs brought back in gpurun_out/ into the small text summaries kept under profiles/.
 
   python tools/ncu_summary.py launches gpurun_out/launches_rN.csv > profiles/launches_rN.txt
-  python tools/ncu_summary.py kernel   gpurun_out/icp_rN.ncu-rep   > profiles/icp_rN.txt
+  python tools/ncu_summary.py kernel   gpurun_out/icp_rN.ncu-rep [profiles/icp_system_traffic.json] > profiles/icp_rN.txt
 """
 import collections
 import csv
@@ -22,6 +22,9 @@ METRICS = [
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+    "l1tex__t_sectors.sum", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
@@ -48,11 +51,30 @@ def launches(path):
         print("%-44s n=%4d  total %9.1f us  avg %8.2f us  share %5.1f%%" % (k[:44], c, v, v / c, 100 * v / tot))
 
 
-def kernel(path):
+def _to_bytes(value, unit):
+    v = float(value.replace(",", ""))
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    return v * scale.get(unit, 1)
+
+
+def kernel(path, json_out=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     print("# ncu --set full --clock-control none --import-source on; source: %s" % path)
+    if json_out:
+        # per-launch DRAM traffic of the captured kernel, the `traffic` figure bench.py reports
+        import json
+        r = rows[2]
+        rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        l2 = hdr.index("l1tex__m_xbar2l1tex_read_bytes.sum")
+        info = {"kernel": r[hdr.index("Kernel Name")], "source": path,
+                "dram_bytes_read": _to_bytes(r[rd], units[rd]), "dram_bytes_write": _to_bytes(r[wr], units[wr]),
+                "l2_to_sm_bytes": _to_bytes(r[l2], units[l2]),
+                "ncu_duration_us": float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")),
+                "grid": r[hdr.index("launch__grid_size")], "block": r[hdr.index("launch__block_size")]}
+        info["traffic_bytes"] = info["dram_bytes_read"] + info["dram_bytes_write"]
+        json.dump(info, open(json_out, "w"), indent=1)
     for r in rows[2:]:
         print("kernel: %s  (id %s)" % (r[hdr.index("Kernel Name")], r[0]))
         for m in METRICS:
@@ -62,4 +84,4 @@ def kernel(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](*sys.argv[2:])
