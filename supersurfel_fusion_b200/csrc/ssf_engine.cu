@@ -4,6 +4,7 @@
 // enqueued on one stream and replayed as a CUDA graph: no per-frame allocation, no
 // intermediate device synchronisation, one small read-back at the end of the frame.
 #include "ssf_engine.h"
+#include "ssf_math.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -30,6 +31,7 @@ struct FrameReport {
 
 __global__ void frame_end_kernel(Counters* counters, const DevicePose* pose, const IcpState* icp, FrameReport* rep,
                                  int advance) {
+  pdl_sync();
   rep->counters = *counters;
   rep->pose = *pose;
   rep->icp_active = icp->active;
@@ -41,6 +43,7 @@ __global__ void frame_end_kernel(Counters* counters, const DevicePose* pose, con
 }
 
 __global__ void split_lmap_kernel(const int2* lmap, float* slanted, size_t n) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) slanted[i] = __int_as_float(lmap[i].y);
 }
@@ -73,7 +76,7 @@ static void enqueue_frame(EngineImpl* e) {
   launch_icp_loop(e);
   launch_icp_finish(e, true);
   launch_fuse(e);
-  frame_end_kernel<<<1, 1, 0, e->stream>>>(e->counters, e->pose, e->icp, e->d_report, 1);
+  launch_pdl(e, frame_end_kernel, dim3(1), dim3(1), 0, e->counters, e->pose, e->icp, e->d_report, 1);
   e->launches++;
 }
 
@@ -113,7 +116,7 @@ static int copy_members(EngineImpl* e, const SsfSurfels& dst, const SsfSurfels& 
 }
 
 static int read_report(EngineImpl* e, bool advance) {
-  frame_end_kernel<<<1, 1, 0, e->stream>>>(e->counters, e->pose, e->icp, e->d_report, advance ? 1 : 0);
+  launch_pdl(e, frame_end_kernel, dim3(1), dim3(1), 0, e->counters, e->pose, e->icp, e->d_report, advance ? 1 : 0);
   e->launches++;
   SSF_CUDA(e, cudaMemcpyAsync(e->h_report, e->d_report, sizeof(FrameReport), cudaMemcpyDeviceToHost, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -193,6 +196,10 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   cudaGetDeviceProperties(&prop, device);
   const int sms = prop.multiProcessorCount;
   const int need_blocks = (e->cap + icp_chunk_size() - 1) / icp_chunk_size();
+  // measured on B200 at VGA (300 frames): 0.563 ms/frame without, 0.582 ms/frame with PDL edges in the
+  // frame graph -- the chain is bound by each kernel's own dependent L2 round trips, not by launch gaps
+  e->pdl = 0;
+  if (const char* v = getenv("SSF_PDL")) e->pdl = atoi(v) != 0;
   e->icp_occ = 3;
   if (const char* v = getenv("SSF_ICP_OCC")) e->icp_occ = atoi(v);   // tuning knob: 3, 4 or 5
   if (e->icp_occ < 3 || e->icp_occ > 5) e->icp_occ = 3;
@@ -482,7 +489,7 @@ int ssf_get_segmentation(SsfHandle h, int32_t* labels, int32_t* bound, uint8_t* 
   if (slanted_depth) {
     int rc = ensure_scratch(e, N * 4);
     if (rc) return rc;
-    split_lmap_kernel<<<(unsigned)((N + 255) / 256), 256, 0, e->stream>>>(e->lmap, reinterpret_cast<float*>(e->scratch), N);
+    launch_pdl(e, split_lmap_kernel, dim3((unsigned)((N + 255) / 256)), dim3(256), 0, e->lmap, reinterpret_cast<float*>(e->scratch), N);
     e->launches++;
     SSF_CUDA(e, cudaMemcpyAsync(slanted_depth, e->scratch, N * 4, cudaMemcpyDefault, e->stream));
   }

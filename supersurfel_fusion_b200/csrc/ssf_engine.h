@@ -121,6 +121,7 @@ struct Engine {
   IcpState* icp;
   float* icp_partials;   // [grid][32]
   int icp_grid;
+  int pdl;               // 1: kernels are chained by programmatic dependent launch (SSF_PDL, default 0: measured slower)
   int icp_occ;           // resident CTAs per SM the system kernel is compiled for
   int icp_stages;        // depth of its TMA-fed shared-memory ring (SSF_ICP_STAGES, default 3)
   int icp_debug;         // profiling knob, see IcpArgs::debug
@@ -141,6 +142,25 @@ struct Engine {
   void* scratch;         // AoS <-> planar conversion buffer
   size_t scratch_bytes;
 };
+
+// Every kernel of the library is launched through here.  With e->pdl the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization, which (also under stream capture, as
+// a programmatic graph edge) lets the kernel start while its predecessor drains; the
+// kernels order themselves with pdl_sync() (ssf_math.cuh).
+template <typename... P, typename... A>
+inline void launch_pdl(Engine* e, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = e->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = e->pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, P(args)...);
+}
 
 // ---- stage launchers (each enqueues on e->stream, no host sync) -----------------
 int icp_chunk_size();     // supersurfels one CTA of the system kernel consumes per grid-stride step

@@ -13,6 +13,17 @@
 
 namespace ssf {
 
+// Programmatic dependent launch (PDL), an option (SSF_PDL=1): the frame is a chain of ~110
+// small dependent kernels.  Every kernel starts by (1) letting the next kernel in
+// the stream / graph begin launching right away and (2) waiting until every kernel before
+// it has completed and its writes are visible -- so the next kernel's CTAs are already
+// resident and parked at their own wait when this one finishes.  Both instructions are
+// no-ops for a kernel launched without the attribute (see launch_pdl, ssf_engine.h).
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 struct V3 { float x, y, z; };
 struct Sym3 { float xx, xy, xz, yy, yz, zz; };   // symmetric 3x3 (reference: Cov3, matrix_types.h:26-31)
 struct M3 { V3 r0, r1, r2; };                     // rows (reference: Mat33, matrix_types.h:33-36)

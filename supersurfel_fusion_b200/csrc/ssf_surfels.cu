@@ -60,6 +60,7 @@ __device__ __forceinline__ V3 pose_t(const DevicePose* p) { return v3(p->t[0], p
 __global__ void extract_accumulate_kernel(const int2* __restrict__ lmap, const unsigned char* __restrict__ inliers,
                                           const int* __restrict__ bound, const uchar4* __restrict__ rgba,
                                           unsigned long long* __restrict__ xsums, CamK cam) {
+  pdl_sync();
   // blockDim.x == 32: a warp is 32 consecutive pixels of one row
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -111,6 +112,7 @@ __device__ __forceinline__ void write_frame_tables(const SurfelSet& frame, float
 __global__ void extract_finalize_kernel(SurfelSet frame, float4* ftab, unsigned long long* xsums,
                                         unsigned char* matched, unsigned long long* best, float z_min,
                                         float z_max, const Counters* counters, int S) {
+  pdl_sync();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= S) return;
   unsigned long long* a = xsums + (size_t)k * 16;
@@ -154,6 +156,7 @@ __global__ void extract_finalize_kernel(SurfelSet frame, float4* ftab, unsigned 
 
 __global__ void frame_tables_kernel(SurfelSet frame, float4* ftab, unsigned char* matched,
                                     unsigned long long* best, int S) {
+  pdl_sync();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= S) return;
   matched[k] = 0;
@@ -162,18 +165,21 @@ __global__ void frame_tables_kernel(SurfelSet frame, float4* ftab, unsigned char
 }
 
 __global__ void model_lab_kernel(SurfelSet model, int n) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   stv(model, P_LAB, i, rgb_to_lab(ldv(model, P_COL, i)));
 }
 
 __global__ void build_lmap_kernel(int2* lmap, const int* labels, const float* slanted, size_t n) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   lmap[i] = make_int2(labels[i], __float_as_int(slanted[i]));
 }
 
 __global__ void invalidate_kernel(SurfelSet frame, float4* ftab, const uint8_t* mask, int S) {
+  pdl_sync();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= S || !mask[k]) return;
   frame.plane(P_CONF)[k] = -1.0f;
@@ -186,6 +192,7 @@ __global__ void associate_kernel(SurfelSet model, SurfelSet frame, const float4*
                                  const int2* __restrict__ lmap, unsigned char* matched, unsigned long long* best,
                                  const DevicePose* pose, const Counters* counters, CamK cam, float z_min,
                                  float z_max) {
+  pdl_sync();
   const int n = counters->nb_supersurfels > 0 ? counters->nb_visible : 0;
   const M3 R = pose_R(pose);
   const V3 t = pose_t(pose);
@@ -216,6 +223,7 @@ __global__ void associate_kernel(SurfelSet model, SurfelSet frame, const float4*
 // updateSupersurfels (supersurfel_fusion_kernels.cu:601-682)
 __global__ void update_kernel(SurfelSet model, SurfelSet frame, const unsigned char* matched,
                               const unsigned long long* best, const DevicePose* pose, Counters* counters, int S) {
+  pdl_sync();
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= S) return;
   if (counters->nb_supersurfels <= 0 || counters->nb_visible <= 0) return;
@@ -270,6 +278,7 @@ constexpr int INS_THREADS = 1024;
 __global__ void __launch_bounds__(INS_THREADS) insert_kernel(SurfelSet model, SurfelSet frame,
                                                               const unsigned char* matched, const DevicePose* pose,
                                                               Counters* counters, int* skip_filter, int S, int cap) {
+  pdl_sync();
   __shared__ int warp_sums[INS_THREADS / 32];
   __shared__ int running;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -376,6 +385,7 @@ __global__ void __launch_bounds__(PART_THREADS) cull_kernel(SurfelSet model, int
                                                             const Counters* counters, const int* skip_filter,
                                                             CamK cam, int delta_t, float conf_thresh, float z_min,
                                                             float z_max) {
+  pdl_sync();
   if (*skip_filter) return;
   const int n = counters->nb_supersurfels;
   const int base = blockIdx.x * PART_CHUNK;
@@ -411,6 +421,7 @@ __global__ void __launch_bounds__(PART_THREADS) cull_kernel(SurfelSet model, int
 // and the new counters (supersurfel_fusion.cu:463-475).  One CTA.
 __global__ void __launch_bounds__(1024) partition_scan_kernel(int* block_hist, Counters* counters,
                                                                const int* skip_filter) {
+  pdl_sync();
   if (*skip_filter) return;
   const int n = counters->nb_supersurfels;
   const int nblocks = (n + PART_CHUNK - 1) / PART_CHUNK;
@@ -479,6 +490,7 @@ __global__ void __launch_bounds__(PART_THREADS) partition_scatter_kernel(SurfelS
                                                                          const int* states, const int* block_off,
                                                                          const Counters* counters,
                                                                          const int* skip_filter) {
+  pdl_sync();
   if (*skip_filter) return;
   const int n = counters->pad;
   const int base = blockIdx.x * PART_CHUNK;
@@ -521,6 +533,7 @@ __global__ void __launch_bounds__(PART_THREADS) partition_scatter_kernel(SurfelS
 
 __global__ void partition_copyback_kernel(SurfelSet src, SurfelSet dst, const Counters* counters,
                                           const int* skip_filter) {
+  pdl_sync();
   if (*skip_filter) return;
   const int n = counters->pad;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -533,6 +546,7 @@ __global__ void partition_copyback_kernel(SurfelSet src, SurfelSet dst, const Co
 }
 
 __global__ void fuse_begin_kernel(Counters* counters) {
+  pdl_sync();
   counters->nb_matched = 0;
   counters->nb_inserted = 0;
   counters->nb_removed = 0;
@@ -542,6 +556,7 @@ __global__ void fuse_begin_kernel(Counters* counters) {
 struct Members { float* pos; float* col; int* stamps; float* ori; float* shape; float* dims; float* conf; };
 
 __global__ void pack_kernel(SurfelSet set, Members d, int n) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (d.pos) for (int k = 0; k < 3; k++) d.pos[3 * (size_t)i + k] = set.plane(P_POS + k)[i];
@@ -554,6 +569,7 @@ __global__ void pack_kernel(SurfelSet set, Members d, int n) {
 }
 
 __global__ void unpack_kernel(Members s, SurfelSet set, int n) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (s.pos) for (int k = 0; k < 3; k++) set.plane(P_POS + k)[i] = s.pos[3 * (size_t)i + k];
@@ -567,6 +583,7 @@ __global__ void unpack_kernel(Members s, SurfelSet set, int n) {
 
 // applyTransformSuperSurfel (supersurfel_fusion_kernels.cu:469-488)
 __global__ void transform_model_kernel(SurfelSet model, const Counters* counters, DevicePose tf) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= counters->nb_supersurfels) return;
   const M3 R = m3(v3(tf.R[0], tf.R[1], tf.R[2]), v3(tf.R[3], tf.R[4], tf.R[5]), v3(tf.R[6], tf.R[7], tf.R[8]));
@@ -580,6 +597,7 @@ __global__ void transform_model_kernel(SurfelSet model, const Counters* counters
 // by atomic ticket, as in the reference.
 __global__ void local_cloud_kernel(SurfelSet model, Counters* counters, const DevicePose* pose, float conf_thresh,
                                    float radius, float* out_pos, float* out_nrm, int capacity) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= counters->nb_supersurfels) return;
   if (!(model.plane(P_CONF)[i] >= conf_thresh)) return;
@@ -596,6 +614,7 @@ __global__ void local_cloud_kernel(SurfelSet model, Counters* counters, const De
 
 // renderBoundaryImage_kernel (TPS_RGBD_kernels.cu:616-643)
 __global__ void preview_kernel(uint8_t* out, const uchar4* rgba, const int* labels, int W, int H) {
+  pdl_sync();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
@@ -615,31 +634,31 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 void launch_extract(Engine* e) {
   const CamK cam = cam_of(e);
   dim3 blk(32, 8), grd(cdiv(e->W, 32), cdiv(e->H, 8));
-  extract_accumulate_kernel<<<grd, blk, 0, e->stream>>>(e->lmap, e->inliers, e->bound, e->rgba, e->xsums, cam);
-  extract_finalize_kernel<<<cdiv(e->S, 128), 128, 0, e->stream>>>(e->frame, e->ftab, e->xsums, e->matched, e->best,
+  launch_pdl(e, extract_accumulate_kernel, dim3(grd), dim3(blk), 0, e->lmap, e->inliers, e->bound, e->rgba, e->xsums, cam);
+  launch_pdl(e, extract_finalize_kernel, dim3(cdiv(e->S, 128)), dim3(128), 0, e->frame, e->ftab, e->xsums, e->matched, e->best,
                                                                  e->cfg.range_min, e->cfg.range_max, e->counters,
                                                                  e->S);
   e->launches += 2;
 }
 
 void launch_frame_tables(Engine* e) {
-  frame_tables_kernel<<<cdiv(e->S, 128), 128, 0, e->stream>>>(e->frame, e->ftab, e->matched, e->best, e->S);
+  launch_pdl(e, frame_tables_kernel, dim3(cdiv(e->S, 128)), dim3(128), 0, e->frame, e->ftab, e->matched, e->best, e->S);
   e->launches++;
 }
 
 void launch_model_lab(Engine* e, int n) {
   if (n <= 0) return;
-  model_lab_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(e->model, n);
+  launch_pdl(e, model_lab_kernel, dim3(cdiv(n, 256)), dim3(256), 0, e->model, n);
   e->launches++;
 }
 
 void launch_build_lmap(Engine* e, const float* slanted_dev) {
-  build_lmap_kernel<<<(unsigned)((e->npix + 255) / 256), 256, 0, e->stream>>>(e->lmap, e->labels, slanted_dev, e->npix);
+  launch_pdl(e, build_lmap_kernel, dim3((unsigned)((e->npix + 255) / 256)), dim3(256), 0, e->lmap, e->labels, slanted_dev, e->npix);
   e->launches++;
 }
 
 void launch_invalidate(Engine* e, const uint8_t* mask_dev) {
-  invalidate_kernel<<<cdiv(e->S, 128), 128, 0, e->stream>>>(e->frame, e->ftab, mask_dev, e->S);
+  launch_pdl(e, invalidate_kernel, dim3(cdiv(e->S, 128)), dim3(128), 0, e->frame, e->ftab, mask_dev, e->S);
   e->launches++;
 }
 
@@ -648,21 +667,21 @@ void launch_fuse(Engine* e) {
   int* skip = e->scan_tmp;            // [0] skip flag, block histograms from [4]
   int* hist = e->scan_tmp + 4;
   const int cap_blocks = cdiv(e->cap, PART_CHUNK);
-  fuse_begin_kernel<<<1, 1, 0, e->stream>>>(e->counters);
-  associate_kernel<<<cdiv(e->cap, 256) < 1184 ? cdiv(e->cap, 256) : 1184, 256, 0, e->stream>>>(
+  launch_pdl(e, fuse_begin_kernel, dim3(1), dim3(1), 0, e->counters);
+  launch_pdl(e, associate_kernel, dim3(cdiv(e->cap, 256) < 1184 ? cdiv(e->cap, 256) : 1184), dim3(256), 0, 
       e->model, e->frame, e->ftab, e->lmap, e->matched, e->best, e->pose, e->counters, cam, e->cfg.range_min,
       e->cfg.range_max);
-  update_kernel<<<cdiv(e->S, 128), 128, 0, e->stream>>>(e->model, e->frame, e->matched, e->best, e->pose,
+  launch_pdl(e, update_kernel, dim3(cdiv(e->S, 128)), dim3(128), 0, e->model, e->frame, e->matched, e->best, e->pose,
                                                         e->counters, e->S);
-  insert_kernel<<<1, INS_THREADS, 0, e->stream>>>(e->model, e->frame, e->matched, e->pose, e->counters, skip, e->S,
+  launch_pdl(e, insert_kernel, dim3(1), dim3(INS_THREADS), 0, e->model, e->frame, e->matched, e->pose, e->counters, skip, e->S,
                                                   e->cap);
-  cull_kernel<<<cap_blocks, PART_THREADS, 0, e->stream>>>(e->model, e->states, hist, e->lmap, e->pose, e->counters,
+  launch_pdl(e, cull_kernel, dim3(cap_blocks), dim3(PART_THREADS), 0, e->model, e->states, hist, e->lmap, e->pose, e->counters,
                                                           skip, cam, e->cfg.delta_t, e->cfg.conf_thresh,
                                                           e->cfg.range_min, e->cfg.range_max);
-  partition_scan_kernel<<<1, 1024, 0, e->stream>>>(hist, e->counters, skip);
-  partition_scatter_kernel<<<cap_blocks, PART_THREADS, 0, e->stream>>>(e->model, e->model_alt, e->states, hist,
+  launch_pdl(e, partition_scan_kernel, dim3(1), dim3(1024), 0, hist, e->counters, skip);
+  launch_pdl(e, partition_scatter_kernel, dim3(cap_blocks), dim3(PART_THREADS), 0, e->model, e->model_alt, e->states, hist,
                                                                        e->counters, skip);
-  partition_copyback_kernel<<<cdiv(e->cap, 256), 256, 0, e->stream>>>(e->model_alt, e->model, e->counters, skip);
+  launch_pdl(e, partition_copyback_kernel, dim3(cdiv(e->cap, 256)), dim3(256), 0, e->model_alt, e->model, e->counters, skip);
   e->launches += 8;
 }
 
@@ -673,13 +692,13 @@ static Members members_of(const SsfSurfels& s) {
 
 void launch_pack(Engine* e, const SurfelSet& set, int n, const SsfSurfels& dst_dev) {
   if (n <= 0) return;
-  pack_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(set, members_of(dst_dev), n);
+  launch_pdl(e, pack_kernel, dim3(cdiv(n, 256)), dim3(256), 0, set, members_of(dst_dev), n);
   e->launches++;
 }
 
 void launch_unpack(Engine* e, const SsfSurfels& src_dev, int n, const SurfelSet& set) {
   if (n <= 0) return;
-  unpack_kernel<<<cdiv(n, 256), 256, 0, e->stream>>>(members_of(src_dev), set, n);
+  launch_pdl(e, unpack_kernel, dim3(cdiv(n, 256)), dim3(256), 0, members_of(src_dev), set, n);
   e->launches++;
 }
 
@@ -687,19 +706,19 @@ void launch_transform_model(Engine* e, const float* R, const float* t) {
   DevicePose tf;
   for (int i = 0; i < 9; i++) tf.R[i] = R[i];
   for (int i = 0; i < 3; i++) tf.t[i] = t[i];
-  transform_model_kernel<<<cdiv(e->cap, 256), 256, 0, e->stream>>>(e->model, e->counters, tf);
+  launch_pdl(e, transform_model_kernel, dim3(cdiv(e->cap, 256)), dim3(256), 0, e->model, e->counters, tf);
   e->launches++;
 }
 
 void launch_local_cloud(Engine* e, float radius, float* pos_dev, float* nrm_dev, int capacity) {
-  local_cloud_kernel<<<cdiv(e->cap, 256), 256, 0, e->stream>>>(e->model, e->counters, e->pose, e->cfg.conf_thresh,
+  launch_pdl(e, local_cloud_kernel, dim3(cdiv(e->cap, 256)), dim3(256), 0, e->model, e->counters, e->pose, e->cfg.conf_thresh,
                                                                radius, pos_dev, nrm_dev, capacity);
   e->launches++;
 }
 
 void launch_preview(Engine* e, uint8_t* bgr_dev) {
   dim3 blk(32, 8), grd(cdiv(e->W, 32), cdiv(e->H, 8));
-  preview_kernel<<<grd, blk, 0, e->stream>>>(bgr_dev, e->rgba, e->labels, e->W, e->H);
+  launch_pdl(e, preview_kernel, dim3(grd), dim3(blk), 0, bgr_dev, e->rgba, e->labels, e->W, e->H);
   e->launches++;
 }
 

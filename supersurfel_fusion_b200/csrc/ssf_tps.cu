@@ -75,6 +75,7 @@ __device__ __forceinline__ void add64(long long* p, long long v) {
 // grid cell; the cell's sums come from an in-CTA reduction.
 __global__ void __launch_bounds__(256) tps_seed_kernel(TpsArgs a, const uint8_t* __restrict__ rgb, size_t rgb_stride,
                                                        const float* __restrict__ depth, size_t depth_stride) {
+  pdl_sync();
   const int cellx = blockIdx.x % a.gx, celly = blockIdx.x / a.gx;
   const int index = blockIdx.x;
   const int x0 = cellx * a.cell, y0 = celly * a.cell;
@@ -199,6 +200,7 @@ struct SpCached {
 
 template <bool DISP>
 __global__ void tps_merge_kernel(TpsArgs a) {
+  pdl_sync();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < a.S) tps_merge_item<DISP>(a, k);
 }
@@ -420,6 +422,7 @@ __device__ __forceinline__ void tps_pass_item(const TpsArgs& a, const SP& spsrc,
 
 template <bool DISP>
 __global__ void __launch_bounds__(128) tps_pass_kernel(TpsArgs a, int OX, int OY) {
+  pdl_sync();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;   // pair index along the row
   const int ry = blockIdx.y * blockDim.y + threadIdx.y;
   const SpGlobal src = {a.sp};
@@ -514,6 +517,7 @@ __device__ __forceinline__ void tps_pass_pixel(const TpsArgs& a, const SP& spsrc
 
 // ---- RANSAC plane initialisation (TPS_RGBD_kernels.cu:318-467, 112-190) --------------
 __global__ void tps_rng_init_kernel(curandState* states, int n) {
+  pdl_sync();
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id < n) curand_init(1234, id, 0, &states[id]);
 }
@@ -568,6 +572,7 @@ __device__ __forceinline__ void tps_init_sample_item(const TpsArgs& a, float4* s
 
 __global__ void tps_init_samples_kernel(TpsArgs a, float4* samples, int* votes, curandState* states, int nbWalks,
                                         float radius) {
+  pdl_sync();
   tps_init_sample_item(a, samples, votes, states, nbWalks, radius, blockIdx.x, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
@@ -601,6 +606,7 @@ __device__ __forceinline__ void tps_eval_row_item(const TpsArgs& a, const float4
 }
 
 __global__ void tps_eval_samples_kernel(TpsArgs a, const float4* samples, int* votes, int nbSamples) {
+  pdl_sync();
   // blockDim.x == 32: a warp is one 32-pixel row segment
   tps_eval_row_item(a, samples, votes, nbSamples, blockIdx.x * blockDim.x + threadIdx.x,
                     blockIdx.y * blockDim.y + threadIdx.y);
@@ -621,6 +627,7 @@ __device__ __forceinline__ void tps_select_item(const TpsArgs& a, float4* sample
 }
 
 __global__ void tps_select_samples_kernel(TpsArgs a, float4* samples, const int* votes, int nbSamples) {
+  pdl_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < a.S) tps_select_item(a, samples, votes, nbSamples, idx);
 }
@@ -662,6 +669,7 @@ __device__ __forceinline__ void tps_init_disp_item(const TpsArgs& a, int ransac,
 }
 
 __global__ void tps_init_disp_kernel(TpsArgs a, int ransac) {
+  pdl_sync();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   tps_init_disp_item(a, ransac, x, y, x < a.W && y < a.H);   // blockDim.x == 32
@@ -733,6 +741,7 @@ __device__ __forceinline__ void tps_filter_finish_item(const TpsArgs& a, const f
 // single-CTA version (multi-kernel path)
 __global__ void __launch_bounds__(1024) tps_filter_kernel(TpsArgs a, float* bufA, float* bufB, int iters, float alpha,
                                                           float beta, float threshold) {
+  pdl_sync();
   for (int i = threadIdx.x; i < a.S; i += blockDim.x) tps_filter_init_item(a, bufA, i);
   __syncthreads();
   float* cur = bufA;
@@ -755,6 +764,7 @@ __device__ __forceinline__ void tps_render_item(const TpsArgs& a, int2* lmap, in
 }
 
 __global__ void tps_render_kernel(TpsArgs a, int2* lmap) {
+  pdl_sync();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x < a.W && y < a.H) tps_render_item(a, lmap, x, y);
@@ -858,6 +868,7 @@ __device__ __forceinline__ void tps_phase_merge_global(const TpsArgs& a, GridBar
 }
 
 __global__ void __launch_bounds__(TPS_PERSIST_THREADS, 1) tps_persistent_kernel(TpsArgs a, TpsRun r) {
+  pdl_sync();
   GridBarrier grid;
   grid.ticket = r.barrier;
   grid.target = 0;   // the ticket is zeroed by a memset node ahead of this kernel
@@ -945,7 +956,7 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 void tps_init_rng(Engine* e) {
   const int n = e->S * e->cfg.nb_samples;
-  tps_rng_init_kernel<<<cdiv(n, 128), 128, 0, e->stream>>>(reinterpret_cast<curandState*>(e->rng), n);
+  launch_pdl(e, tps_rng_init_kernel, dim3(cdiv(n, 128)), dim3(128), 0, reinterpret_cast<curandState*>(e->rng), n);
   e->launches++;
 }
 
@@ -979,7 +990,7 @@ int tps_persistent_grid(int device, int gx, int gy, int cell, int height, int nb
 void launch_ingest(Engine* e, const uint8_t* rgb_dev, size_t rgb_stride, const float* depth_dev,
                    size_t depth_stride) {
   TpsArgs a = tps_args(e);
-  tps_seed_kernel<<<e->S, 256, 0, e->stream>>>(a, rgb_dev, rgb_stride, depth_dev, depth_stride);
+  launch_pdl(e, tps_seed_kernel, dim3(e->S), dim3(256), 0, a, rgb_dev, rgb_stride, depth_dev, depth_stride);
   e->launches++;
 }
 
@@ -989,8 +1000,8 @@ static void launch_pass(Engine* e, const TpsArgs& a, int OX, int OY) {
   // (fusing the merge into the pass as "last CTA done" was measured 40 % slower per frame: one
   // CTA merging 1200 superpixels serialises five dependent L2 round trips)
   dim3 blk(32, 4), grd(cdiv(pairs, 32), cdiv(a.raw_h, 4));
-  tps_pass_kernel<DISP><<<grd, blk, 0, e->stream>>>(a, OX, OY);
-  tps_merge_kernel<DISP><<<cdiv(a.S, 128), 128, 0, e->stream>>>(a);
+  launch_pdl(e, tps_pass_kernel<DISP>, dim3(grd), dim3(blk), 0, a, OX, OY);
+  launch_pdl(e, tps_merge_kernel<DISP>, dim3(cdiv(a.S, 128)), dim3(128), 0, a);
   e->launches += 2;
 }
 
@@ -1027,17 +1038,17 @@ void launch_tps(Engine* e) {
   dim3 blk(32, 8), grd(cdiv(e->W, 32), cdiv(e->H, 8));
   if (e->cfg.seg_use_ransac) {
     int* votes = reinterpret_cast<int*>(e->samples + (size_t)e->S * e->cfg.nb_samples);
-    tps_init_samples_kernel<<<e->S, e->cfg.nb_samples, 0, e->stream>>>(
+    launch_pdl(e, tps_init_samples_kernel, dim3(e->S), dim3(e->cfg.nb_samples), 0, 
         a, e->samples, votes, reinterpret_cast<curandState*>(e->rng), 10, (float)e->cfg.cell_size / 2.f);
-    tps_eval_samples_kernel<<<grd, blk, 0, e->stream>>>(a, e->samples, votes, e->cfg.nb_samples);
-    tps_select_samples_kernel<<<cdiv(e->S, 128), 128, 0, e->stream>>>(a, e->samples, votes, e->cfg.nb_samples);
-    tps_init_disp_kernel<<<grd, blk, 0, e->stream>>>(a, 1);
+    launch_pdl(e, tps_eval_samples_kernel, dim3(grd), dim3(blk), 0, a, e->samples, votes, e->cfg.nb_samples);
+    launch_pdl(e, tps_select_samples_kernel, dim3(cdiv(e->S, 128)), dim3(128), 0, a, e->samples, votes, e->cfg.nb_samples);
+    launch_pdl(e, tps_init_disp_kernel, dim3(grd), dim3(blk), 0, a, 1);
     e->launches += 4;
   } else {
-    tps_init_disp_kernel<<<grd, blk, 0, e->stream>>>(a, 0);
+    launch_pdl(e, tps_init_disp_kernel, dim3(grd), dim3(blk), 0, a, 0);
     e->launches += 1;
   }
-  tps_merge_kernel<true><<<cdiv(a.S, 128), 128, 0, e->stream>>>(a);
+  launch_pdl(e, tps_merge_kernel<true>, dim3(cdiv(a.S, 128)), dim3(128), 0, a);
   e->launches++;
   for (int k = nbIters / 2; k < nbIters; k++) {
     launch_pass<true>(e, a, 0, 0);
@@ -1045,9 +1056,9 @@ void launch_tps(Engine* e) {
     launch_pass<true>(e, a, 0, 1);
     launch_pass<true>(e, a, 1, 0);
   }
-  tps_filter_kernel<<<1, 1024, 0, e->stream>>>(a, e->filt_a, e->filt_b, e->cfg.filter_iter, e->cfg.filter_alpha,
+  launch_pdl(e, tps_filter_kernel, dim3(1), dim3(1024), 0, a, e->filt_a, e->filt_b, e->cfg.filter_iter, e->cfg.filter_alpha,
                                                e->cfg.filter_beta, e->cfg.filter_threshold);
-  tps_render_kernel<<<grd, blk, 0, e->stream>>>(a, e->lmap);
+  launch_pdl(e, tps_render_kernel, dim3(grd), dim3(blk), 0, a, e->lmap);
   e->launches += 2;
 }
 
