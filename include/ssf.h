@@ -132,10 +132,30 @@ int ssf_is_initialized(SsfHandle h);
 #define SSF_FLAG_BILATERAL 1u
 int ssf_process_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth,
                       size_t depth_stride, const float* pose_prior_Rt12, uint32_t flags);
+/* Same with the 16-bit depth image of the TUM / live drivers: decodes
+ * depth.convertTo(CV_32FC1, depth_scale) on the device
+ * (node/supersurfel_fusion_rgbd_benchmark_node.cpp:609-610; node/supersurfel_fusion_node.cpp
+ * does the same with its depth_scale parameter).  depth_stride in BYTES. */
+int ssf_process_frame_depth16(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const uint16_t* depth16,
+                              size_t depth_stride, float depth_scale, const float* pose_prior_Rt12,
+                              uint32_t flags);
 /* Same, inputs already resident on the handle's device (dense, stride = width). */
 int ssf_process_frame_device(SsfHandle h, const uint8_t* rgb_dev, const float* depth_dev,
                              const float* pose_prior_Rt12, uint32_t flags);
 int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out);
+
+/* ---- ingest (supersurfel_fusion.cu:171-181) -------------------------------- */
+/* cv::cuda::bilateralFilter(depth, depth, kernel_size, sigma_color, sigma_spatial)
+ * (supersurfel_fusion.cu:180 calls it with -1, 0.03, 4.5), out of place; host-or-device
+ * pointers, H x W floats.  SSF_FLAG_BILATERAL runs it inside ssf_process_frame*. */
+int ssf_bilateral_filter(SsfHandle h, const float* depth, size_t depth_stride, int kernel_size,
+                         float sigma_color, float sigma_spatial, float* out);
+/* The filtered depth of the last frame processed with SSF_FLAG_BILATERAL (what the
+ * reference downloads for its VO, supersurfel_fusion.cu:181). */
+int ssf_get_filtered_depth(SsfHandle h, float* depth);
+/* cv::cuda::cvtColor(rgb, gray, CV_RGB2GRAY) of the last frame's colour image
+ * (supersurfel_fusion.cu:175-177; consumed by the out-of-scope VO / MOD). */
+int ssf_get_gray(SsfHandle h, uint8_t* gray);
 
 /* ---- getters (supersurfel_fusion.hpp:85-91) ------------------------------ */
 int ssf_get_pose(SsfHandle h, float R[9], float t[3]);          /* getPose() */

@@ -119,6 +119,12 @@ void orc_engine_get_frame(const OrcEngine*, OrcSurfels* out /* caller buffers, S
 OrcTps* orc_engine_tps(OrcEngine*);
 void orc_set_num_threads(int n);
 
+/* ---- ingest in front of the path (supersurfel_fusion.cu:171-181; oracle_ingest.cpp) */
+void orc_bilateral_filter(const float* depth, int width, int height, int kernel_size, float sigma_color,
+                          float sigma_spatial, float* out);
+void orc_rgb_to_gray(const uint8_t* rgb, int n_pixels, uint8_t* gray);
+void orc_depth16_to_metres(const uint16_t* depth16, int n_pixels, float scale, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -280,5 +280,29 @@ class Engine:
             self.h = None
 
 
+def bilateral_filter(depth, kernel_size=-1, sigma_color=0.03, sigma_spatial=4.5):
+    """cv::cuda::bilateralFilter(depth, depth, -1, 0.03, 4.5) restated out of place (oracle_ingest.cpp)."""
+    depth = _f32(depth)
+    out = np.empty_like(depth)
+    h, w = depth.shape
+    lib().orc_bilateral_filter(_p(depth), C.c_int(w), C.c_int(h), C.c_int(kernel_size), C.c_float(sigma_color),
+                               C.c_float(sigma_spatial), _p(out))
+    return out
+
+
+def rgb_to_gray(rgb):
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    out = np.empty(rgb.shape[:2], np.uint8)
+    lib().orc_rgb_to_gray(_p(rgb), C.c_int(out.size), _p(out))
+    return out
+
+
+def depth16_to_metres(depth16, scale):
+    depth16 = np.ascontiguousarray(depth16, np.uint16)
+    out = np.empty(depth16.shape, np.float32)
+    lib().orc_depth16_to_metres(_p(depth16), C.c_int(out.size), C.c_float(scale), _p(out))
+    return out
+
+
 def set_num_threads(n):
     lib().orc_set_num_threads(C.c_int(n))

@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libssf.so")
-SOURCES = ["ssf_icp.cu", "ssf_surfels.cu", "ssf_tps.cu", "ssf_engine.cu"]
+SOURCES = ["ssf_icp.cu", "ssf_surfels.cu", "ssf_tps.cu", "ssf_ingest.cu", "ssf_engine.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -49,12 +49,12 @@ __global__ void split_lmap_kernel(const int2* lmap, float* slanted, size_t n) {
 }
 
 struct EngineImpl : public SsfEngine {
-  uint64_t launches_per_frame;
+  uint64_t launches_per_frame[2];
   FrameReport* d_report;
   FrameReport* h_report;
   float* h_prior;          // pinned 12 floats
-  cudaGraphExec_t graph_exec;
-  bool graph_ready;
+  cudaGraphExec_t graph_exec[2];   // [0] depth used as given, [1] SSF_FLAG_BILATERAL
+  bool graph_ready[2];
   bool use_graph;
   bool created;
 };
@@ -68,8 +68,17 @@ static cudaError_t dalloc(T** p, size_t count) {
   return err;
 }
 
-static void enqueue_frame(EngineImpl* e) {
-  launch_ingest(e, e->in_rgb, (size_t)e->W * 3, e->in_depth, (size_t)e->W * 4);
+// the reference's filter arguments (supersurfel_fusion.cu:180)
+static const int kBilateralKernel = -1;
+static const float kBilateralSigmaColor = 0.03f, kBilateralSigmaSpatial = 4.5f;
+
+static void enqueue_frame(EngineImpl* e, bool bilateral) {
+  const float* depth = e->in_depth;
+  if (bilateral) {
+    launch_bilateral(e, e->in_depth, e->depth_f, kBilateralKernel, kBilateralSigmaColor, kBilateralSigmaSpatial);
+    depth = e->depth_f;
+  }
+  launch_ingest(e, e->in_rgb, (size_t)e->W * 3, depth, (size_t)e->W * 4);
   launch_tps(e);
   launch_extract(e);
   launch_icp_begin_from_pose(e);
@@ -183,7 +192,7 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   e->cfg = *cfg;
   e->device = device;
   e->launches = 0;
-  e->graph_ready = false;
+  e->graph_ready[0] = e->graph_ready[1] = false;
   e->use_graph = true;
   e->created = false;
   e->W = cfg->cam.width; e->H = cfg->cam.height;
@@ -226,6 +235,7 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   const int S = e->S, nbs = cfg->nb_samples;
   A(dalloc(&e->rgba, N)); A(dalloc(&e->disp, N)); A(dalloc(&e->labels, N)); A(dalloc(&e->bound, N));
   A(dalloc(&e->inliers, N)); A(dalloc(&e->lmap, N)); A(dalloc(&e->in_rgb, N * 3)); A(dalloc(&e->in_depth, N));
+  A(dalloc(&e->depth_f, N)); A(dalloc(&e->in_depth16, N));
   A(dalloc(&e->sp, (size_t)S)); A(dalloc(&e->sums, (size_t)S));
   {
     char* p = nullptr;
@@ -282,10 +292,11 @@ int ssf_destroy(SsfHandle h) {
   EngineImpl* e = static_cast<EngineImpl*>(h);
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
-  if (e->graph_ready) cudaGraphExecDestroy(e->graph_exec);
+  for (int k = 0; k < 2; k++)
+    if (e->graph_ready[k]) cudaGraphExecDestroy(e->graph_exec[k]);
   for (int g = 0; g < SSF_MAX_PEERS; g++)
     if (e->xpeer_open[g]) cudaIpcCloseMemHandle(e->xpeer_open[g]);
-  void* bufs[] = {e->rgba, e->disp, e->labels, e->bound, e->inliers, e->lmap, e->in_rgb, e->in_depth, e->sp, e->sums,
+  void* bufs[] = {e->rgba, e->disp, e->labels, e->bound, e->inliers, e->lmap, e->in_rgb, e->in_depth, e->depth_f, e->in_depth16, e->sp, e->sums,
                   e->samples, e->rng, e->filt_a, e->filt_b, e->xsums, e->tps_barrier, e->tps_trace, e->xbuf, e->xpeers_dev, e->frame.base, e->model.base,
                   e->model_alt.base, e->ftab, e->matched, e->best, e->states, e->scan_tmp, e->icp, e->icp_partials,
                   e->counters, e->pose, e->d_report, e->scratch};
@@ -307,7 +318,8 @@ int ssf_set_stream(SsfHandle h, void* cuda_stream) {
   H_CHECK(h);
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
-  if (e->graph_ready) { cudaGraphExecDestroy(e->graph_exec); e->graph_ready = false; }
+  for (int k = 0; k < 2; k++)
+    if (e->graph_ready[k]) { cudaGraphExecDestroy(e->graph_exec[k]); e->graph_ready[k] = false; }
   return SSF_OK;
 }
 
@@ -319,29 +331,29 @@ const char* ssf_last_error(SsfHandle h) {
 int ssf_is_initialized(SsfHandle h) { return (h && static_cast<EngineImpl*>(h)->created) ? 1 : 0; }
 
 static int run_frame(EngineImpl* e, const float* prior, uint32_t flags) {
-  if (flags & SSF_FLAG_BILATERAL) { e->err = "SSF_FLAG_BILATERAL: ingest filter not built yet"; return SSF_ERR_INVALID_ARG; }
+  const int gi = (flags & SSF_FLAG_BILATERAL) ? 1 : 0;
   if (prior) {
     memcpy(e->h_prior, prior, 12 * sizeof(float));
     SSF_CUDA(e, cudaMemcpyAsync(e->pose, e->h_prior, 12 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
   }
   SSF_CUDA(e, cudaEventRecord(e->evf0, e->stream));
   if (e->use_graph) {
-    if (!e->graph_ready) {
+    if (!e->graph_ready[gi]) {
       cudaGraph_t g;
       const uint64_t before = e->launches;
       SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-      enqueue_frame(e);
+      enqueue_frame(e, gi != 0);
       SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
-      e->launches_per_frame = e->launches - before;
+      e->launches_per_frame[gi] = e->launches - before;
       e->launches = before;
-      SSF_CUDA(e, cudaGraphInstantiate(&e->graph_exec, g, 0));
+      SSF_CUDA(e, cudaGraphInstantiate(&e->graph_exec[gi], g, 0));
       cudaGraphDestroy(g);
-      e->graph_ready = true;
+      e->graph_ready[gi] = true;
     }
-    SSF_CUDA(e, cudaGraphLaunch(e->graph_exec, e->stream));
-    e->launches += e->launches_per_frame;
+    SSF_CUDA(e, cudaGraphLaunch(e->graph_exec[gi], e->stream));
+    e->launches += e->launches_per_frame[gi];
   } else {
-    enqueue_frame(e);
+    enqueue_frame(e, gi != 0);
   }
   SSF_CUDA(e, cudaEventRecord(e->evf1, e->stream));
   SSF_CUDA(e, cudaMemcpyAsync(e->h_report, e->d_report, sizeof(FrameReport), cudaMemcpyDeviceToHost, e->stream));
@@ -373,6 +385,54 @@ int ssf_process_frame_device(SsfHandle h, const uint8_t* rgb_dev, const float* d
   SSF_CUDA(e, cudaMemcpyAsync(e->in_rgb, rgb_dev, e->npix * 3, cudaMemcpyDeviceToDevice, e->stream));
   SSF_CUDA(e, cudaMemcpyAsync(e->in_depth, depth_dev, e->npix * 4, cudaMemcpyDeviceToDevice, e->stream));
   return run_frame(e, pose_prior_Rt12, flags);
+}
+
+int ssf_process_frame_depth16(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const uint16_t* depth16,
+                              size_t depth_stride, float depth_scale, const float* pose_prior_Rt12, uint32_t flags) {
+  H_CHECK(h);
+  if (!rgb || !depth16) return SSF_ERR_INVALID_ARG;
+  if (rgb_stride == 0) rgb_stride = (size_t)e->W * 3;
+  if (depth_stride == 0) depth_stride = (size_t)e->W * 2;
+  if (rgb_stride < (size_t)e->W * 3 || depth_stride < (size_t)e->W * 2) return SSF_ERR_INVALID_ARG;
+  SSF_CUDA(e, cudaMemcpy2DAsync(e->in_rgb, (size_t)e->W * 3, rgb, rgb_stride, (size_t)e->W * 3, e->H, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpy2DAsync(e->in_depth16, (size_t)e->W * 2, depth16, depth_stride, (size_t)e->W * 2, e->H, cudaMemcpyDefault, e->stream));
+  // depth.convertTo(CV_32FC1, depth_scale) (node/supersurfel_fusion_rgbd_benchmark_node.cpp:609-610)
+  launch_depth16(e, e->in_depth16, e->in_depth, depth_scale);
+  return run_frame(e, pose_prior_Rt12, flags);
+}
+
+int ssf_bilateral_filter(SsfHandle h, const float* depth, size_t depth_stride, int kernel_size, float sigma_color,
+                         float sigma_spatial, float* out) {
+  H_CHECK(h);
+  if (!depth || !out) return SSF_ERR_INVALID_ARG;
+  if (depth_stride == 0) depth_stride = (size_t)e->W * 4;
+  SSF_CUDA(e, cudaMemcpy2DAsync(e->in_depth, (size_t)e->W * 4, depth, depth_stride, (size_t)e->W * 4, e->H, cudaMemcpyDefault, e->stream));
+  int rc = launch_bilateral(e, e->in_depth, e->depth_f, kernel_size, sigma_color, sigma_spatial);
+  if (rc) { e->err = "ssf_bilateral_filter: kernel radius above the supported 12"; return rc; }
+  SSF_CUDA(e, cudaMemcpyAsync(out, e->depth_f, e->npix * 4, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_CUDA(e, cudaGetLastError());
+  return SSF_OK;
+}
+
+int ssf_get_gray(SsfHandle h, uint8_t* gray) {
+  H_CHECK(h);
+  if (!gray) return SSF_ERR_INVALID_ARG;
+  int rc = ensure_scratch(e, e->npix);
+  if (rc) return rc;
+  launch_gray(e, e->in_rgb, reinterpret_cast<uint8_t*>(e->scratch));
+  SSF_CUDA(e, cudaMemcpyAsync(gray, e->scratch, e->npix, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_CUDA(e, cudaGetLastError());
+  return SSF_OK;
+}
+
+int ssf_get_filtered_depth(SsfHandle h, float* depth) {
+  H_CHECK(h);
+  if (!depth) return SSF_ERR_INVALID_ARG;
+  SSF_CUDA(e, cudaMemcpyAsync(depth, e->depth_f, e->npix * 4, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  return SSF_OK;
 }
 
 int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out) {

@@ -94,6 +94,7 @@ struct Engine {
   uint8_t* in_rgb;       // staging for the raw inputs
   float* in_depth;
   float* depth_f;        // bilateral-filtered depth (optional ingest)
+  uint16_t* in_depth16;  // staging of a 16-bit depth image (ssf_process_frame_depth16)
 
   // TPS
   Superpixel* sp;
@@ -163,6 +164,11 @@ inline void launch_pdl(Engine* e, void (*kernel)(P...), dim3 grid, dim3 block, s
 }
 
 // ---- stage launchers (each enqueues on e->stream, no host sync) -----------------
+// ingest (ssf_ingest.cu)
+int launch_bilateral(Engine* e, const float* src_dev, float* dst_dev, int kernel_size, float sigma_color,
+                     float sigma_spatial);
+void launch_gray(Engine* e, const uint8_t* rgb_dev, uint8_t* gray_dev);
+void launch_depth16(Engine* e, const uint16_t* d16_dev, float* out_dev, float scale);
 int icp_chunk_size();     // supersurfels one CTA of the system kernel consumes per grid-stride step
 int icp_ctas_per_sm();
 int icp_configure(int stages);   // opts the system kernel in to its shared-memory ring; returns the clamped depth    // resident CTAs per SM the system kernel is compiled for

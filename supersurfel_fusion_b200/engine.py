@@ -58,10 +58,13 @@ class SsfFrameStats(C.Structure):
                 ("icp_inliers", C.c_float), ("icp_error", C.c_double), ("gpu_ms", C.c_float)]
 
 
+SSF_FLAG_BILATERAL = 1   # include/ssf.h
+
 # every symbol include/ssf.h declares
 EXPORTS = [
     "ssf_config_default", "ssf_create", "ssf_destroy", "ssf_set_stream", "ssf_last_error", "ssf_is_initialized",
-    "ssf_process_frame", "ssf_process_frame_device", "ssf_get_frame_stats", "ssf_get_pose", "ssf_set_pose",
+    "ssf_process_frame", "ssf_process_frame_depth16", "ssf_process_frame_device", "ssf_bilateral_filter",
+    "ssf_get_filtered_depth", "ssf_get_gray", "ssf_get_frame_stats", "ssf_get_pose", "ssf_set_pose",
     "ssf_get_stamp", "ssf_set_stamp", "ssf_get_counts", "ssf_get_nb_superpixels", "ssf_copy_model",
     "ssf_copy_frame", "ssf_get_segmentation", "ssf_render_preview", "ssf_get_slanted_depth", "ssf_export_model",
     "ssf_extract_local_point_cloud", "ssf_invalidate_frame_supersurfels", "ssf_transform_model", "ssf_set_model",
@@ -90,6 +93,12 @@ def load_library():
                 fn.restype = C.c_int
         lib.ssf_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
                                           C.c_uint32]
+        lib.ssf_process_frame_depth16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_float,
+                                                  C.c_void_p, C.c_uint32]
+        lib.ssf_bilateral_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_float,
+                                             C.c_void_p]
+        lib.ssf_get_filtered_depth.argtypes = [C.c_void_p, C.c_void_p]
+        lib.ssf_get_gray.argtypes = [C.c_void_p, C.c_void_p]
         lib.ssf_process_frame_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         lib.ssf_tps_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         lib.ssf_icp_system.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -242,6 +251,43 @@ class SupersurfelFusion:
         rc = self._lib.ssf_process_frame(self._h, _ptr(rgb_h), rs, _ptr(depth_h), ds, _ptr(prior), flags)
         self._check(rc, "ssf_process_frame")
         return self.getFrameStats()
+
+    def processFrameDepth16(self, rgb_h, depth16_h, depth_scale, pose_prior=None, flags=0):
+        """processFrame on the raw 16-bit depth image of the TUM / live drivers: the
+        depth.convertTo(CV_32FC1, depth_scale) of the node runs on the device."""
+        prior = None
+        if pose_prior is not None:
+            R, t = pose_prior
+            prior = np.concatenate([np.asarray(R, np.float32).reshape(9), np.asarray(t, np.float32).reshape(3)])
+        rgb_h = np.ascontiguousarray(rgb_h, np.uint8)
+        depth16_h = np.ascontiguousarray(depth16_h, np.uint16)
+        if rgb_h.shape[:2] != (self.height, self.width) or depth16_h.shape != (self.height, self.width):
+            raise SsfError("image size does not match the camera")
+        rc = self._lib.ssf_process_frame_depth16(self._h, _ptr(rgb_h), self.width * 3, _ptr(depth16_h), self.width * 2,
+                                                 float(depth_scale), _ptr(prior), flags)
+        self._check(rc, "ssf_process_frame_depth16")
+        return self.getFrameStats()
+
+    # -- ingest (supersurfel_fusion.cu:171-181) -----------------------------------------
+    def bilateralFilter(self, depth, kernel_size=-1, sigma_color=0.03, sigma_spatial=4.5):
+        """cv::cuda::bilateralFilter(depth, depth, -1, 0.03, 4.5) (supersurfel_fusion.cu:180), out of place."""
+        depth = np.ascontiguousarray(depth, np.float32)
+        out = np.empty((self.height, self.width), np.float32)
+        rc = self._lib.ssf_bilateral_filter(self._h, _ptr(depth), self.width * 4, int(kernel_size), float(sigma_color),
+                                            float(sigma_spatial), _ptr(out))
+        self._check(rc, "ssf_bilateral_filter")
+        return out
+
+    def getFilteredDepth(self):
+        out = np.empty((self.height, self.width), np.float32)
+        self._check(self._lib.ssf_get_filtered_depth(self._h, _ptr(out)), "ssf_get_filtered_depth")
+        return out
+
+    def getGray(self):
+        """cv::cuda::cvtColor(rgb, gray, CV_RGB2GRAY) of the last frame (supersurfel_fusion.cu:175-177)."""
+        out = np.empty((self.height, self.width), np.uint8)
+        self._check(self._lib.ssf_get_gray(self._h, _ptr(out)), "ssf_get_gray")
+        return out
 
     def processFrameDevice(self, rgb_dev, depth_dev, pose_prior=None, flags=0):
         prior = None
