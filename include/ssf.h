@@ -246,6 +246,17 @@ int ssf_peer_handle(SsfHandle h, void* handle64);
 int ssf_connect_peers(SsfHandle h, int rank, int world, const void* handles);
 int ssf_icp_tiled(SsfHandle h, const float* R_init, const float* t_init, int src_begin, int src_count,
                   float out29[29], float R_rel[9], float t_rel[3], int* iters, int* valid);
+/* DenseRegistration::align (dense_registration.cu:52-243), the loop-closure registration:
+ * `source` = a keyframe's supersurfels in ITS camera frame (positions, colors, orientations,
+ * confidences are read; host-or-device), target = the handle's current frame (supersurfels,
+ * label map, slanted depth).  R_init/t_init map keyframe-camera to current-camera coordinates.
+ * Whole loop in one kernel launch.  R/t receive the reference's return value (identity/zero
+ * when invalid); pairs = matched pairs of the last iteration; out29 = its (centred, scaled)
+ * system.  Uses the handle's icp_iter / icp_cov_thresh like the reference's shared
+ * DenseRegistration object (supersurfel_fusion.cu:137,776). */
+int ssf_align(SsfHandle h, const SsfSurfels* source, int source_size, const float R_init[9],
+              const float t_init[3], float R[9], float t[3], int* valid, int* iters, int* pairs,
+              float out29[29]);
 /* Model update block of processFrame (supersurfel_fusion.cu:351-483) at the
  * handle's current pose and stamp. */
 int ssf_fuse(SsfHandle h);

@@ -69,6 +69,13 @@ int orc_icp(int n_src, const float* src_pos, const float* src_col, const float* 
             const int32_t* labels, const float* depth, int nb_iter, double cov_thresh,
             float* R_rel9, float* t_rel3, OrcIcpStats* stats);
 
+/* DenseRegistration::align (dense_registration.cu:52-243): keyframe supersurfels (source, with
+ * confidences) against the current frame; returns 1 and (R, t) when valid. */
+int orc_align(int n_src, const float* src_pos, const float* src_col, const float* src_orient,
+              const float* src_conf, const float* tgt_col, const float* tgt_orient, const float* tgt_conf,
+              const float* R_init9, const float* t_init3, const OrcCam* cam, const int32_t* labels,
+              const float* depth, int nb_iter, double cov_thresh, float* R9, float* t3, OrcIcpStats* stats);
+
 /* pose <- pose o (R_rel,t_rel) with quaternion renormalisation (supersurfel_fusion.cu:313-328) */
 void orc_compose_pose(float* R9, float* t3, const float* R_rel9, const float* t_rel3);
 

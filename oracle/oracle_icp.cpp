@@ -346,6 +346,197 @@ extern "C" int orc_icp(int n_src, const float* src_pos, const float* src_col, co
   return valid ? 1 : 0;
 }
 
+
+// ---- loop-closure registration: DenseRegistration::align ----------------------------
+// (core/src/dense_registration.cu:52-243; kernels makeCorrespondences,
+//  core/src/dense_registration_kernels.cu:27-100, and buildSymmetricPoint2PlaneSystem<128>,
+//  core/include/supersurfel_fusion/dense_registration_kernels.cuh:87-173).
+// Source = a keyframe's supersurfels, target = the current frame.  Differences from the
+// frame-to-model loop that are restated as they are: the source confidence IS tested, the
+// depth gate is isfinite() only, normals are re-normalised, the matched pairs are centred and
+// scaled before the system is built, every one of nb_iter iterations runs (no convergence
+// test), the translation gate is 0.3 m, and the returned transform is built from the
+// R_inc / t_inc of the TOP of the last iteration (:90-96 vs :229-238: they are not refreshed
+// after the last update, unlike :411-417 of the frame-to-model loop).
+extern "C" int orc_align(int n_src, const float* src_pos, const float* src_col, const float* src_orient,
+                         const float* src_conf, const float* tgt_col, const float* tgt_orient,
+                         const float* tgt_conf, const float* R_init9, const float* t_init3, const OrcCam* cam,
+                         const int32_t* labels, const float* depth, int nb_iter, double cov_thresh,
+                         float* R9, float* t3, OrcIcpStats* stats) {
+  bool valid = true;
+  int iter = 0, iters_done = 0;
+  double tf_inc[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+  const Mat33 R_init = ldm(R_init9);
+  const f3 t_init = mk3(t_init3[0], t_init3[1], t_init3[2]);
+  Mat33 R_inc = identity33();
+  f3 t_inc = mk3(0, 0, 0);
+  double JtJ[6][6] = {{0}};
+  double Jtr[6] = {0};
+  float sys[29] = {0};
+  int nb_pairs = 0;
+  std::vector<f3> ms_p(n_src), ms_n(n_src), mt_p(n_src), mt_n(n_src);
+  // rgbToLab of the keyframe colours is iteration-invariant
+  std::vector<f3> src_lab(n_src);
+  for (int i = 0; i < n_src; i++) src_lab[i] = rgbToLab(ld3(src_col, i));
+
+  while (iter++ < nb_iter) {
+    iters_done++;
+    R_inc = mkmat(mk3((float)tf_inc[0][0], (float)tf_inc[0][1], (float)tf_inc[0][2]),
+                  mk3((float)tf_inc[1][0], (float)tf_inc[1][1], (float)tf_inc[1][2]),
+                  mk3((float)tf_inc[2][0], (float)tf_inc[2][1], (float)tf_inc[2][2]));
+    t_inc = mk3((float)tf_inc[0][3], (float)tf_inc[1][3], (float)tf_inc[2][3]);
+    const Mat33 R = R_inc * R_init;
+    const f3 t = R_inc * t_init + t_inc;
+
+    // makeCorrespondences + remove_if compaction (kept in source order)
+    nb_pairs = 0;
+    for (int i = 0; i < n_src; i++) {
+      if (!(src_conf[i] > 0.0f)) continue;
+      const f3 p_view = mulf(R, ld3(src_pos, i)) + t;
+      const int u = project_round(p_view.x * cam->fx / p_view.z + cam->cx);
+      const int v = project_round(p_view.y * cam->fy / p_view.z + cam->cy);
+      if (u < 0 || u >= cam->width || v < 0 || v >= cam->height) continue;
+      const int target_id = labels[v * cam->width + u];
+      if (!(tgt_conf[target_id] > 0.0f)) continue;
+      const f3 dl = src_lab[i] - rgbToLab(ld3(tgt_col, target_id));
+      const float dist_color = sqrtf(dotf(dl, dl));
+      const float t_depth = depth[v * cam->width + u];
+      if (!std::isfinite(t_depth)) continue;
+      f3 s_normal = mk3(src_orient[9 * i + 6], src_orient[9 * i + 7], src_orient[9 * i + 8]);
+      s_normal = s_normal * (1.0f / sqrtf(dotf(s_normal, s_normal)));
+      s_normal = mulf(R, s_normal);
+      s_normal = s_normal * (1.0f / sqrtf(dotf(s_normal, s_normal)));
+      f3 t_normal = mk3(tgt_orient[9 * target_id + 6], tgt_orient[9 * target_id + 7], tgt_orient[9 * target_id + 8]);
+      t_normal = t_normal * (1.0f / sqrtf(dotf(t_normal, t_normal)));
+      const f3 t_position = mk3(t_depth * ((float)u - cam->cx) / cam->fx, t_depth * ((float)v - cam->cy) / cam->fy, t_depth);
+      const f3 dd = p_view - t_position;
+      if (dist_color < 20.0f && sqrtf(dotf(dd, dd)) < 0.1f && fabsf(dotf(s_normal, t_normal)) > 0.8f) {
+        ms_p[nb_pairs] = p_view; ms_n[nb_pairs] = s_normal;
+        mt_p[nb_pairs] = t_position; mt_n[nb_pairs] = t_normal;
+        nb_pairs++;
+      }
+    }
+    if (nb_pairs < 100) { valid = false; break; }
+
+    // centroids and isotropic scale of the matched sets (thrust::reduce over floats in an
+    // unspecified tree order in the reference; here the order-free limit: double sums)
+    double cs[3] = {0, 0, 0}, ct[3] = {0, 0, 0};
+    for (int k = 0; k < nb_pairs; k++) {
+      cs[0] += ms_p[k].x; cs[1] += ms_p[k].y; cs[2] += ms_p[k].z;
+      ct[0] += mt_p[k].x; ct[1] += mt_p[k].y; ct[2] += mt_p[k].z;
+    }
+    const float fn = (float)nb_pairs;
+    const f3 source_centroid = mk3((float)cs[0] / fn, (float)cs[1] / fn, (float)cs[2] / fn);
+    const f3 target_centroid = mk3((float)ct[0] / fn, (float)ct[1] / fn, (float)ct[2] / fn);
+    double sc_sum_t = 0.0, sc_sum_s = 0.0;
+    for (int k = 0; k < nb_pairs; k++) {
+      const f3 a = mt_p[k] - target_centroid, b = ms_p[k] - source_centroid;
+      sc_sum_t += (double)dotf(a, a);
+      sc_sum_s += (double)dotf(b, b);
+    }
+    float scale = (float)sc_sum_t;
+    scale += (float)sc_sum_s;
+    scale = sqrtf(scale / (2.0f * fn));
+    scale = 1.0f / scale;
+
+    // buildSymmetricPoint2PlaneSystem<128>
+    double acc[29];
+    for (int k = 0; k < 29; k++) acc[k] = 0.0;
+    for (int k = 0; k < nb_pairs; k++) {
+      const f3 ps = scale * (ms_p[k] - source_centroid);
+      const f3 pt = scale * (mt_p[k] - target_centroid);
+      const f3 ns = ms_n[k] * (1.0f / sqrtf(dotf(ms_n[k], ms_n[k])));
+      const f3 nt = mt_n[k] * (1.0f / sqrtf(dotf(mt_n[k], mt_n[k])));
+      const f3 d = pt - ps;
+      const f3 c1 = mk3(fmaf(pt.y, ns.z, -(pt.z * ns.y)), fmaf(pt.z, ns.x, -(pt.x * ns.z)), fmaf(pt.x, ns.y, -(pt.y * ns.x)));
+      const f3 c2 = mk3(fmaf(ps.y, nt.z, -(ps.z * nt.y)), fmaf(ps.z, nt.x, -(ps.x * nt.z)), fmaf(ps.x, nt.y, -(ps.y * nt.x)));
+      const float dn1 = dotf(d, ns), dn2 = dotf(d, nt);
+      const float x1[6] = {c1.x, c1.y, c1.z, ns.x, ns.y, ns.z};
+      const float x2[6] = {c2.x, c2.y, c2.z, nt.x, nt.y, nt.z};
+      int q = 0;
+      for (int a = 0; a < 6; a++)
+        for (int b = a; b < 6; b++) acc[q++] += (double)(x1[a] * x1[b] + x2[a] * x2[b]);
+      for (int a = 0; a < 6; a++) acc[21 + a] += (double)(dn1 * x1[a] + dn2 * x2[a]);
+      acc[27] += (double)(dn2 * dn2);
+      acc[28] += 1.0;
+    }
+    for (int k = 0; k < 29; k++) sys[k] = (float)acc[k];
+    int q = 0;
+    for (int a = 0; a < 6; a++)
+      for (int b = a; b < 6; b++) { JtJ[a][b] = (double)sys[q]; JtJ[b][a] = (double)sys[q]; q++; }
+    for (int a = 0; a < 6; a++) Jtr[a] = (double)sys[21 + a];
+
+    double Xp[6];
+    ldlt_solve6(JtJ, Jtr, Xp);
+    double tran[3] = {Xp[3], Xp[4], Xp[5]};
+    double axis[3] = {Xp[0], Xp[1], Xp[2]};
+    const double axis_norm = std::sqrt(axis[0] * axis[0] + axis[1] * axis[1] + axis[2] * axis[2]);
+    double angle = (double)(0.5f) * std::atan(axis_norm);
+    if (axis_norm > 0.0) { axis[0] /= axis_norm; axis[1] /= axis_norm; axis[2] /= axis_norm; }   // appendix B9 guard
+    else { axis[0] = 1.0; axis[1] = 0.0; axis[2] = 0.0; angle = 0.0; }
+    const double c = std::cos(angle), sn = std::sin(angle);
+    for (int a = 0; a < 3; a++) { tran[a] /= (double)scale; tran[a] *= c; }
+    double Rr[3][3];
+    {
+      const double sa[3] = {sn * axis[0], sn * axis[1], sn * axis[2]};
+      const double ca[3] = {(1.0 - c) * axis[0], (1.0 - c) * axis[1], (1.0 - c) * axis[2]};
+      double tmp;
+      tmp = ca[0] * axis[1]; Rr[0][1] = tmp - sa[2]; Rr[1][0] = tmp + sa[2];
+      tmp = ca[0] * axis[2]; Rr[0][2] = tmp + sa[1]; Rr[2][0] = tmp - sa[1];
+      tmp = ca[1] * axis[2]; Rr[1][2] = tmp - sa[0]; Rr[2][1] = tmp + sa[0];
+      for (int a = 0; a < 3; a++) Rr[a][a] = ca[a] * axis[a] + c;
+    }
+    // iso_iter = Trans(ct) * Rot * Trans(tran) * Rot * Trans(-cs): linear part Rr*Rr,
+    // translation ct + Rr*tran - (Rr*Rr)*cs; the rotation block alone is then re-normalised
+    double R2[3][3], tf_iter[4][4] = {{0}};
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) R2[a][b] = Rr[a][0] * Rr[0][b] + Rr[a][1] * Rr[1][b] + Rr[a][2] * Rr[2][b];
+    const double csd[3] = {(double)source_centroid.x, (double)source_centroid.y, (double)source_centroid.z};
+    const double ctd[3] = {(double)target_centroid.x, (double)target_centroid.y, (double)target_centroid.z};
+    for (int a = 0; a < 3; a++)
+      tf_iter[a][3] = ctd[a] + (Rr[a][0] * tran[0] + Rr[a][1] * tran[1] + Rr[a][2] * tran[2]) -
+                      (R2[a][0] * csd[0] + R2[a][1] * csd[1] + R2[a][2] * csd[2]);
+    quat_renormalise<double>(R2);
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) tf_iter[a][b] = R2[a][b];
+    tf_iter[3][3] = 1.0;
+    double nt4[4][4];
+    for (int a = 0; a < 4; a++)
+      for (int b = 0; b < 4; b++) {
+        double sum = 0.0;
+        for (int k = 0; k < 4; k++) sum += tf_iter[a][k] * tf_inc[k][b];
+        nt4[a][b] = sum;
+      }
+    std::memcpy(tf_inc, nt4, sizeof(nt4));
+  }
+
+  double diag[6];
+  inverse_diag6(JtJ, diag);
+  for (int a = 0; a < 6; a++)
+    if (diag[a] > cov_thresh) { valid = false; break; }
+  Mat33 R = identity33();
+  f3 t = mk3(0, 0, 0);
+  if (valid) {
+    if (length(t_inc) > 0.3f) valid = false;
+    else {
+      R = transpose(R_inc);          // R_inc / t_inc of the top of the last iteration (see header)
+      t = -(R * t_inc);
+    }
+  }
+  for (int a = 0; a < 3; a++) {
+    R9[3 * a] = R.rows[a].x; R9[3 * a + 1] = R.rows[a].y; R9[3 * a + 2] = R.rows[a].z;
+  }
+  t3[0] = t.x; t3[1] = t.y; t3[2] = t.z;
+  if (stats) {
+    stats->valid = valid ? 1 : 0;
+    stats->iters = iters_done;
+    stats->inliers = (float)nb_pairs;
+    stats->error = sys[28] > 0 ? std::sqrt((double)(sys[27] / sys[28])) : 0.0;
+    std::memcpy(stats->last_system, sys, sizeof(sys));
+  }
+  return valid ? 1 : 0;
+}
+
 extern "C" void orc_compose_pose(float* R9, float* t3, const float* R_rel9, const float* t_rel3) {
   // supersurfel_fusion.cu:313-328 (Eigen::Quaternionf round trip in float)
   Mat33 R = ldm(R9), Rr = ldm(R_rel9);

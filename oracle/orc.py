@@ -164,6 +164,25 @@ def icp(cam, src_pos, src_col, src_orient, tgt_col, tgt_orient, tgt_conf, R_init
                                                error=st.error, system=np.array(st.last_system, np.float32))
 
 
+def align(cam, src_pos, src_col, src_orient, src_conf, tgt_col, tgt_orient, tgt_conf, R_init, t_init, labels, depth,
+          nb_iter=10, cov_thresh=0.04):
+    """DenseRegistration::align (dense_registration.cu:52-243): keyframe -> current frame."""
+    src_pos, src_col, src_orient, src_conf = _f32(src_pos), _f32(src_col), _f32(src_orient), _f32(src_conf)
+    tgt_col, tgt_orient, tgt_conf = _f32(tgt_col), _f32(tgt_orient), _f32(tgt_conf)
+    R_init, t_init = _f32(R_init).reshape(9), _f32(t_init).reshape(3)
+    labels = np.ascontiguousarray(labels, np.int32)
+    depth = _f32(depth)
+    R = np.zeros(9, np.float32)
+    t = np.zeros(3, np.float32)
+    st = OrcIcpStats()
+    lib().orc_align.restype = C.c_int
+    ok = lib().orc_align(C.c_int(len(src_pos)), _p(src_pos), _p(src_col), _p(src_orient), _p(src_conf), _p(tgt_col),
+                         _p(tgt_orient), _p(tgt_conf), _p(R_init), _p(t_init), C.byref(cam), _p(labels),
+                         _p(depth), C.c_int(nb_iter), C.c_double(cov_thresh), _p(R), _p(t), C.byref(st))
+    return bool(ok), R.reshape(3, 3), t, dict(valid=st.valid, iters=st.iters, pairs=st.inliers,
+                                               error=st.error, system=np.array(st.last_system, np.float32))
+
+
 def compose_pose(R, t, R_rel, t_rel):
     R = _f32(R).reshape(9).copy()
     t = _f32(t).reshape(3).copy()

@@ -55,6 +55,8 @@ def lib():
         L.ref_create.restype = C.c_void_p
         L.ref_nb_superpixels.restype = C.c_int
         L.ref_icp.restype = C.c_int
+        L.ref_align.restype = C.c_int
+        L.ref_align.argtypes = None
         L.ref_icp_system_time.restype = C.c_float
         for name in ("ref_destroy", "ref_nb_superpixels", "ref_tps", "ref_get_segmentation", "ref_set_segmentation",
                      "ref_generate", "ref_get_frame", "ref_set_frame", "ref_get_model", "ref_set_model",
@@ -177,6 +179,16 @@ class RefEngine:
         R = np.zeros(9, np.float32)
         t = np.zeros(3, np.float32)
         ok = lib().ref_icp(self.h, _p(Rv), _p(tv), _p(R), _p(t))
+        return bool(ok), R.reshape(3, 3), t
+
+    def align(self, source, R_init, t_init):
+        """DenseRegistration::align: keyframe supersurfels (host) against the harness' current frame."""
+        Ri = np.ascontiguousarray(R_init, np.float32).reshape(9)
+        ti = np.ascontiguousarray(t_init, np.float32).reshape(3)
+        R = np.zeros(9, np.float32)
+        t = np.zeros(3, np.float32)
+        v = _view(source)
+        ok = lib().ref_align(self.h, C.byref(v), C.c_int(len(source.positions)), _p(Ri), _p(ti), _p(R), _p(t))
         return bool(ok), R.reshape(3, 3), t
 
     def fuse(self, stamp):

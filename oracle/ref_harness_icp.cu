@@ -49,4 +49,31 @@ float ref_icp_system_time(RefEngine* e, const float* R9, const float* t3, int n,
   return ms / launches;
 }
 
+// DenseRegistration::align (dense_registration.cu:52-243) exactly as closeGlobalLoop calls it
+// (supersurfel_fusion.cu:776-792): a keyframe's supersurfels, uploaded from the host, against
+// the harness' current frame.
+int ref_align(RefEngine* e, const RefSurfelsHost* src, int n, const float* Rinit9, const float* tinit3, float* R9,
+              float* t3) {
+  thrust::host_vector<float3> hp(n), hc(n);
+  thrust::host_vector<Mat33> ho(n);
+  thrust::host_vector<float> hf(n);
+  for (int i = 0; i < n; i++) {
+    hp[i] = make_float3(src->positions[3 * i], src->positions[3 * i + 1], src->positions[3 * i + 2]);
+    hc[i] = make_float3(src->colors[3 * i], src->colors[3 * i + 1], src->colors[3 * i + 2]);
+    ho[i] = mat_from(src->orientations + 9 * i);
+    hf[i] = src->confidences[i];
+  }
+  thrust::device_vector<float3> dp = hp, dc = hc;
+  thrust::device_vector<Mat33> dorient = ho;
+  thrust::device_vector<float> dconf = hf;
+  Mat33 R;
+  float3 t;
+  const bool ok = e->icp->align(dp, dc, dorient, dconf, e->frame.positions, e->frame.colors, e->frame.orientations,
+                                e->frame.confidences, n, e->texDepth, e->tps->getTexIndex(), mat_from(Rinit9),
+                                make_float3(tinit3[0], tinit3[1], tinit3[2]), e->cam, R, t);
+  for (int r = 0; r < 3; r++) { R9[3 * r] = R.rows[r].x; R9[3 * r + 1] = R.rows[r].y; R9[3 * r + 2] = R.rows[r].z; }
+  t3[0] = t.x; t3[1] = t.y; t3[2] = t.z;
+  return ok ? 1 : 0;
+}
+
 }  // extern "C"

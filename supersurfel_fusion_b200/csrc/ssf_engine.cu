@@ -878,6 +878,47 @@ int ssf_icp_tiled(SsfHandle h, const float* R_init, const float* t_init, int src
   return SSF_OK;
 }
 
+int ssf_align(SsfHandle h, const SsfSurfels* source, int source_size, const float R_init[9], const float t_init[3],
+              float R[9], float t[3], int* valid, int* iters, int* pairs, float out29[29]) {
+  H_CHECK(h);
+  if (!source || source_size <= 0 || !R_init || !t_init || !R || !t) return SSF_ERR_INVALID_ARG;
+  if (!source->positions || !source->colors || !source->orientations || !source->confidences) return SSF_ERR_INVALID_ARG;
+  const size_t n = (size_t)source_size;
+  // scratch: the four source members, then Lab, the matched records, flags and the result block
+  const size_t floats = n * (3 + 3 + 9 + 1 + 3 + 12);
+  const size_t bytes = floats * sizeof(float) + ((n + 15) & ~(size_t)15) + sizeof(AlignResult) + 64;
+  int rc = ensure_scratch(e, bytes);
+  if (rc) return rc;
+  float* pos = reinterpret_cast<float*>(e->scratch);
+  float* col = pos + 3 * n;
+  float* ori = col + 3 * n;
+  float* conf = ori + 9 * n;
+  float* lab = conf + n;
+  float* rec = lab + 3 * n;
+  unsigned char* ok = reinterpret_cast<unsigned char*>(rec + 12 * n);
+  AlignResult* res = reinterpret_cast<AlignResult*>(ok + ((n + 15) & ~(size_t)15));
+  SSF_CUDA(e, cudaMemcpyAsync(pos, source->positions, n * 12, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(col, source->colors, n * 12, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(ori, source->orientations, n * 36, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(conf, source->confidences, n * 4, cudaMemcpyDefault, e->stream));
+  AlignResult init = {};
+  init.lab_sq = icp_lab_gate_sq();
+  init.dist_sq = icp_dist_gate_sq();
+  SSF_CUDA(e, cudaMemcpyAsync(res, &init, sizeof(init), cudaMemcpyHostToDevice, e->stream));
+  launch_align(e, pos, col, ori, conf, source_size, lab, rec, ok, R_init, t_init, res);
+  AlignResult out;
+  SSF_CUDA(e, cudaMemcpyAsync(&out, res, sizeof(out), cudaMemcpyDeviceToHost, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_CUDA(e, cudaGetLastError());
+  memcpy(R, out.R, 36);
+  memcpy(t, out.t, 12);
+  if (valid) *valid = out.valid;
+  if (iters) *iters = out.iters;
+  if (pairs) *pairs = out.pairs;
+  if (out29) memcpy(out29, out.sys, 29 * sizeof(float));
+  return SSF_OK;
+}
+
 int ssf_fuse(SsfHandle h) {
   H_CHECK(h);
   launch_fuse(e);

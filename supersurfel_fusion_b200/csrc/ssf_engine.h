@@ -64,6 +64,14 @@ struct IcpState {
   unsigned int xseq;     // sequence number of the cross-GPU exchange (never reset)
 };
 
+// result block of one loop-closure registration (align_kernel); lab_sq / dist_sq are inputs
+struct AlignResult {
+  float R[9], t[3];
+  int valid, iters, pairs;
+  float sys[29];
+  float lab_sq, dist_sq;
+};
+
 struct Counters {
   int nb_supersurfels, nb_visible, nb_removed, nb_matched, nb_inserted;
   int stamp;
@@ -181,6 +189,10 @@ void launch_icp_build_range(Engine* e, int begin, int count);
 void launch_icp_solve(Engine* e, const float* sys29_dev);
 void launch_icp_tiled_loop(Engine* e, int begin, int count);
 void launch_icp_finish(Engine* e, bool apply_to_pose);
+void launch_align(Engine* e, const float* pos, const float* col, const float* ori, const float* conf, int n,
+                  float* lab, float* rec, unsigned char* ok, const float* Rinit, const float* tinit, AlignResult* out_dev);
+float icp_lab_gate_sq();
+float icp_dist_gate_sq();
 void launch_ingest(Engine* e, const uint8_t* rgb_dev, size_t rgb_stride, const float* depth_dev,
                    size_t depth_stride);
 void launch_tps(Engine* e);

@@ -71,7 +71,7 @@ EXPORTS = [
     "ssf_set_frame", "ssf_set_segmentation", "ssf_tps_segment", "ssf_get_ransac_samples",
     "ssf_generate_supersurfels", "ssf_icp_system", "ssf_icp_system_enqueue", "ssf_icp", "ssf_icp_begin",
     "ssf_icp_build", "ssf_icp_solve", "ssf_icp_finish", "ssf_peer_handle", "ssf_connect_peers", "ssf_icp_tiled",
-    "ssf_fuse",
+    "ssf_fuse", "ssf_align",
     "ssf_timer_start", "ssf_timer_stop", "ssf_synchronize", "ssf_get_launch_count",
 ]
 
@@ -104,6 +104,7 @@ def load_library():
         lib.ssf_icp_system.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.ssf_icp_system_enqueue.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.ssf_icp.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+        lib.ssf_align.argtypes = [C.c_void_p] + [C.c_void_p, C.c_int] + [C.c_void_p] * 8
         lib.ssf_set_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.ssf_copy_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         lib.ssf_copy_frame.argtypes = [C.c_void_p, C.c_void_p]
@@ -503,6 +504,22 @@ class SupersurfelFusion:
                                      _ptr(R), _ptr(t), C.byref(iters), C.byref(valid))
         self._check(rc, "ssf_icp_tiled")
         return bool(valid.value), R.reshape(3, 3), t, dict(iters=iters.value, valid=valid.value, system=sys29)
+
+    def align(self, source, R_init, t_init):
+        """DenseRegistration::align (dense_registration.cu:52-243): registers a keyframe's
+        supersurfels (`source`, a Supersurfels in the keyframe's camera frame) against the
+        current frame.  Returns (valid, R, t, stats)."""
+        Ri = np.ascontiguousarray(R_init, np.float32).reshape(9)
+        ti = np.ascontiguousarray(t_init, np.float32).reshape(3)
+        R = np.zeros(9, np.float32)
+        t = np.zeros(3, np.float32)
+        sys29 = np.zeros(29, np.float32)
+        valid, iters, pairs = C.c_int(0), C.c_int(0), C.c_int(0)
+        view = source.view()
+        rc = self._lib.ssf_align(self._h, C.byref(view), len(source.positions), _ptr(Ri), _ptr(ti), _ptr(R), _ptr(t),
+                                 C.byref(valid), C.byref(iters), C.byref(pairs), _ptr(sys29))
+        self._check(rc, "ssf_align")
+        return bool(valid.value), R.reshape(3, 3), t, dict(iters=iters.value, pairs=pairs.value, system=sys29)
 
     def fuse(self):
         self._check(self._lib.ssf_fuse(self._h), "ssf_fuse")
