@@ -192,6 +192,27 @@ int ssf_invalidate_frame_supersurfels(SsfHandle h, const uint8_t* mask);
  * supersurfel_fusion_kernels.cu:469-488). */
 int ssf_transform_model(SsfHandle h, const float R[9], const float t[3]);
 
+/* Loop-closure hook: DeformationGraph::applyGraphToModel -> applyDeformation
+ * (deformation_graph.cu:840-861, deformation_graph_kernels.cu:27-73): warp the first
+ * model_size model supersurfels by an embedded deformation graph computed by the caller.
+ * nodes_*: nb_nodes rows (positions [3], rotations [9] row-major, translations [3]);
+ * neighbours_weights [model_size][4], neighbours_idx [model_size][4] (the four nearest
+ * nodes of every supersurfel, VertexMap of deformation_graph_types.hpp).  Host-or-device. */
+int ssf_apply_deformation(SsfHandle h, const float* nodes_positions, const float* nodes_rotations,
+                          const float* nodes_translations, int nb_nodes, const float* neighbours_weights,
+                          const int32_t* neighbours_idx, int model_size);
+/* ---- consumer formats (the wire / disk formats after the path) ----------------------- */
+/* publishModelMarker / publishFrameMarker geometry (node/supersurfel_fusion_node.cpp:303-413,
+ * 415-520): per supersurfel 6 points [3] (two triangles of the +-3 sqrt(dims) quad along e1/e2)
+ * and 6 RGBA colours [4] (colour / 255, alpha 1); zeros / black below conf_thresh.
+ * which: 0 = model (nb_supersurfels rows), 1 = frame.  *count = rows available. */
+int ssf_get_markers(SsfHandle h, int which, float conf_thresh, float* points, float* colors, int capacity,
+                    int* count);
+/* One line of the TUM trajectory file the benchmark node writes
+ * (node/supersurfel_fusion_rgbd_benchmark_node.cpp:727-729):
+ * "timestamp tx ty tz qx qy qz qw\n" of the current pose. */
+int ssf_format_tum_pose(SsfHandle h, const char* timestamp, char* line, size_t line_size);
+
 /* ---- stage entry points (for parity tests and callers that drive stages) --- */
 /* State injection: host-or-device arrays in the layouts above. */
 int ssf_set_model(SsfHandle h, const SsfSurfels* src, int nb_supersurfels, int nb_visible);

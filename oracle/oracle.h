@@ -126,6 +126,14 @@ void orc_engine_get_frame(const OrcEngine*, OrcSurfels* out /* caller buffers, S
 OrcTps* orc_engine_tps(OrcEngine*);
 void orc_set_num_threads(int n);
 
+/* ---- consumers of the model (oracle_consumers.cpp) */
+void orc_apply_deformation(float* positions, float* orientations, float* shapes, const float* node_pos,
+                           const float* node_rot, const float* node_trans, const float* weights,
+                           const int32_t* nn, int model_size);
+void orc_markers(const float* positions, const float* colors, const float* orientations, const float* dims,
+                 const float* confidences, int n, float conf_thresh, float* points, float* out_colors);
+int orc_format_tum_pose(const float* R9, const float* t3, const char* timestamp, char* line, int line_size);
+
 /* ---- ingest in front of the path (supersurfel_fusion.cu:171-181; oracle_ingest.cpp) */
 void orc_bilateral_filter(const float* depth, int width, int height, int kernel_size, float sigma_color,
                           float sigma_spatial, float* out);

@@ -323,5 +323,29 @@ def depth16_to_metres(depth16, scale):
     return out
 
 
+def apply_deformation(surfels, node_pos, node_rot, node_trans, weights, nn):
+    """applyDeformation (deformation_graph_kernels.cu:27-73), in place on a Surfels."""
+    node_pos, node_rot, node_trans, weights = _f32(node_pos), _f32(node_rot), _f32(node_trans), _f32(weights)
+    nn = np.ascontiguousarray(nn, np.int32)
+    lib().orc_apply_deformation(_p(surfels.positions), _p(surfels.orientations), _p(surfels.shapes), _p(node_pos),
+                                _p(node_rot), _p(node_trans), _p(weights), _p(nn), C.c_int(len(surfels.positions)))
+
+
+def markers(surfels, conf_thresh):
+    """publishModelMarker geometry (node/supersurfel_fusion_node.cpp:303-413): (points [n,6,3], colors [n,6,4])."""
+    n = len(surfels.positions)
+    pts = np.zeros((n, 6, 3), np.float32)
+    col = np.zeros((n, 6, 4), np.float32)
+    lib().orc_markers(_p(surfels.positions), _p(surfels.colors), _p(surfels.orientations), _p(surfels.dims),
+                      _p(surfels.confidences), C.c_int(n), C.c_float(conf_thresh), _p(pts), _p(col))
+    return pts, col
+
+
+def format_tum_pose(R, t, timestamp):
+    buf = C.create_string_buffer(256)
+    lib().orc_format_tum_pose(_p(_f32(R).reshape(9)), _p(_f32(t).reshape(3)), timestamp.encode(), buf, C.c_int(256))
+    return buf.value.decode()
+
+
 def set_num_threads(n):
     lib().orc_set_num_threads(C.c_int(n))

@@ -919,6 +919,98 @@ int ssf_align(SsfHandle h, const SsfSurfels* source, int source_size, const floa
   return SSF_OK;
 }
 
+int ssf_apply_deformation(SsfHandle h, const float* nodes_positions, const float* nodes_rotations,
+                          const float* nodes_translations, int nb_nodes, const float* neighbours_weights,
+                          const int32_t* neighbours_idx, int model_size) {
+  H_CHECK(h);
+  if (!nodes_positions || !nodes_rotations || !nodes_translations || !neighbours_weights || !neighbours_idx ||
+      nb_nodes <= 0 || model_size < 0 || model_size > e->cap)
+    return SSF_ERR_INVALID_ARG;
+  if (model_size == 0) return SSF_OK;
+  const size_t nn = (size_t)nb_nodes, n = (size_t)model_size;
+  const size_t bytes = nn * (3 + 9 + 3) * 4 + n * 32 + 64;
+  int rc = ensure_scratch(e, bytes);
+  if (rc) return rc;
+  // 16-byte aligned first: the float4 / int4 per-supersurfel tables
+  float* w = reinterpret_cast<float*>(e->scratch);
+  int* idx = reinterpret_cast<int*>(w + 4 * n);
+  float* gp = reinterpret_cast<float*>(idx + 4 * n);
+  float* gr = gp + 3 * nn;
+  float* gt = gr + 9 * nn;
+  SSF_CUDA(e, cudaMemcpyAsync(w, neighbours_weights, n * 16, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(idx, neighbours_idx, n * 16, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(gp, nodes_positions, nn * 12, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(gr, nodes_rotations, nn * 36, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(gt, nodes_translations, nn * 12, cudaMemcpyDefault, e->stream));
+  launch_apply_deformation(e, gp, gr, gt, w, idx, model_size, nb_nodes);
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_CUDA(e, cudaGetLastError());
+  return SSF_OK;
+}
+
+int ssf_get_markers(SsfHandle h, int which, float conf_thresh, float* points, float* colors, int capacity, int* count) {
+  H_CHECK(h);
+  if (!points || !colors || capacity < 0 || (which != 0 && which != 1)) return SSF_ERR_INVALID_ARG;
+  int n = e->S;
+  if (which == 0) {
+    int rc = read_report(e, false);
+    if (rc) return rc;
+    n = e->h_report->counters.nb_supersurfels;
+  }
+  if (count) *count = n;
+  if (n > capacity) n = capacity;
+  if (n == 0) return SSF_OK;
+  int rc = ensure_scratch(e, (size_t)n * (18 + 24) * 4);
+  if (rc) return rc;
+  float* dp = reinterpret_cast<float*>(e->scratch);
+  float* dc = dp + (size_t)n * 18;
+  launch_markers(e, which == 1, n, conf_thresh, dp, dc);
+  SSF_CUDA(e, cudaMemcpyAsync(points, dp, (size_t)n * 72, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(colors, dc, (size_t)n * 96, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_CUDA(e, cudaGetLastError());
+  return SSF_OK;
+}
+
+// tf::Matrix3x3::getRotation (the quaternion the nodes publish and write): Shoemake's method in
+// double, as in tf's LinearMath/Matrix3x3.h
+static void rotation_to_tf_quaternion(const float R[9], double q[4]) {
+  const double m[3][3] = {{R[0], R[1], R[2]}, {R[3], R[4], R[5]}, {R[6], R[7], R[8]}};
+  const double trace = m[0][0] + m[1][1] + m[2][2];
+  if (trace > 0.0) {
+    double s = sqrt(trace + 1.0);
+    q[3] = s * 0.5;
+    s = 0.5 / s;
+    q[0] = (m[2][1] - m[1][2]) * s;
+    q[1] = (m[0][2] - m[2][0]) * s;
+    q[2] = (m[1][0] - m[0][1]) * s;
+  } else {
+    const int i = m[0][0] < m[1][1] ? (m[1][1] < m[2][2] ? 2 : 1) : (m[0][0] < m[2][2] ? 2 : 0);
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    double s = sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0);
+    q[i] = s * 0.5;
+    s = 0.5 / s;
+    q[3] = (m[k][j] - m[j][k]) * s;
+    q[j] = (m[j][i] + m[i][j]) * s;
+    q[k] = (m[k][i] + m[i][k]) * s;
+  }
+}
+
+int ssf_format_tum_pose(SsfHandle h, const char* timestamp, char* line, size_t line_size) {
+  H_CHECK(h);
+  if (!timestamp || !line || line_size == 0) return SSF_ERR_INVALID_ARG;
+  int rc = read_report(e, false);
+  if (rc) return rc;
+  double q[4];
+  rotation_to_tf_quaternion(e->h_report->pose.R, q);
+  const float* t = e->h_report->pose.t;
+  // operator<< of doubles: "%g" (6 significant digits), as the benchmark node's trajectory_file
+  // (node/supersurfel_fusion_rgbd_benchmark_node.cpp:727-729); tf stores the origin in double
+  const int w = snprintf(line, line_size, "%s %g %g %g %g %g %g %g\n", timestamp, (double)t[0], (double)t[1], (double)t[2],
+                         q[0], q[1], q[2], q[3]);
+  return (w < 0 || (size_t)w >= line_size) ? SSF_ERR_INVALID_ARG : SSF_OK;
+}
+
 int ssf_fuse(SsfHandle h) {
   H_CHECK(h);
   launch_fuse(e);

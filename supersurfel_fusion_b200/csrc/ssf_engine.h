@@ -172,6 +172,9 @@ inline void launch_pdl(Engine* e, void (*kernel)(P...), dim3 grid, dim3 block, s
 }
 
 // ---- stage launchers (each enqueues on e->stream, no host sync) -----------------
+void launch_apply_deformation(Engine* e, const float* node_pos, const float* node_rot, const float* node_trans,
+                              const float* weights, const int* nn, int n, int n_nodes);
+void launch_markers(Engine* e, bool frame, int n, float conf_thresh, float* points_dev, float* colors_dev);
 // ingest (ssf_ingest.cu)
 int launch_bilateral(Engine* e, const float* src_dev, float* dst_dev, int kernel_size, float sigma_color,
                      float sigma_spatial);

@@ -593,6 +593,124 @@ __global__ void transform_model_kernel(SurfelSet model, const Counters* counters
   sts(model, i, rotate_sym(R, lds(model, i)));
 }
 
+// ---- consumers of the model ---------------------------
+// applyDeformation (core/src/deformation_graph_kernels.cu:27-73): warps every model
+// supersurfel by the embedded deformation graph -- blend of its four nearest nodes' rigid
+// motions, rotations blended as weighted quaternions -- position, orientation and shape.
+// quatToRotMat / rotMatToQuat are restated with the reference's own quirks
+// (matrix_math.cuh:512-585: `wy` is computed as w*z, and the non-positive-trace branch picks
+// index 2 when m22 exceeds EITHER other diagonal entry).
+__device__ __forceinline__ float4 rot_to_quat(const M3& m) {
+  float4 q;
+  float s;
+  const float trace = m.r0.x + m.r1.y + m.r2.z;
+  if (trace > 0) {
+    s = sqrtf(trace + 1);
+    q.w = 0.5f * s;
+    s = 0.5f / s;
+    q.x = (m.r2.y - m.r1.z) * s;
+    q.y = (m.r0.z - m.r2.x) * s;
+    q.z = (m.r1.x - m.r0.y) * s;
+  } else {
+    int i = 0;
+    if (m.r1.y > m.r0.x) i = 1;
+    if (m.r2.z > m.r0.x || m.r2.z > m.r1.y) i = 2;
+    if (i == 0) {
+      s = sqrtf(1.0f + m.r0.x - m.r1.y - m.r2.z);
+      q.x = 0.5f * s; s = 0.5f / s;
+      q.w = (m.r2.y - m.r1.z) * s; q.y = (m.r0.y + m.r1.x) * s; q.z = (m.r0.z + m.r2.x) * s;
+    } else if (i == 1) {
+      s = sqrtf(1.0f + m.r1.y - m.r0.x - m.r2.z);
+      q.y = 0.5f * s; s = 0.5f / s;
+      q.w = (m.r0.z - m.r2.x) * s; q.x = (m.r0.y + m.r1.x) * s; q.z = (m.r1.z + m.r2.y) * s;
+    } else {
+      s = sqrtf(1.0f + m.r2.z - m.r0.x - m.r1.y);
+      q.z = 0.5f * s; s = 0.5f / s;
+      q.w = (m.r1.x - m.r0.y) * s; q.x = (m.r0.z + m.r2.x) * s; q.y = (m.r1.z + m.r2.y) * s;
+    }
+  }
+  return q;
+}
+__device__ __forceinline__ M3 quat_to_rot(float4 q) {
+  const float x2 = q.x * q.x, y2 = q.y * q.y, z2 = q.z * q.z;
+  const float xy = q.x * q.y, xz = q.x * q.z, yz = q.y * q.z;
+  const float wx = q.w * q.x, wy = q.w * q.z /* sic, matrix_math.cuh:521 */, wz = q.w * q.z;
+  return m3(v3(1.0f - 2.0f * (y2 + z2), 2.0f * (xy - wz), 2.0f * (xz + wy)),
+            v3(2.0f * (xy + wz), 1.0f - 2.0f * (x2 + z2), 2.0f * (yz - wx)),
+            v3(2.0f * (xz - wy), 2.0f * (yz + wx), 1.0f - 2.0f * (x2 + y2)));
+}
+
+__global__ void apply_deformation_kernel(SurfelSet model, const float* __restrict__ node_pos,
+                                         const float* __restrict__ node_rot, const float* __restrict__ node_trans,
+                                         const float4* __restrict__ weights, const int4* __restrict__ nn, int n, int n_nodes) {
+  pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 w4 = weights[i];
+  const int4 id4 = nn[i];
+  const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+  const int id[4] = {id4.x, id4.y, id4.z, id4.w};
+  const V3 pi = ldv(model, P_POS, i);
+  V3 po = v3(0.f, 0.f, 0.f);
+  float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int node = min(max(id[k], 0), n_nodes - 1);      // the reference indexes unchecked
+    const V3 gk = v3(node_pos[3 * node], node_pos[3 * node + 1], node_pos[3 * node + 2]);
+    const V3 tk = v3(node_trans[3 * node], node_trans[3 * node + 1], node_trans[3 * node + 2]);
+    const float* r = node_rot + 9 * node;
+    const M3 Rk = m3(v3(r[0], r[1], r[2]), v3(r[3], r[4], r[5]), v3(r[6], r[7], r[8]));
+    const float4 qk = rot_to_quat(Rk);
+    po = po + w[k] * (Rk * (pi - gk) + gk + tk);
+    bq.x += w[k] * qk.x; bq.y += w[k] * qk.y; bq.z += w[k] * qk.z; bq.w += w[k] * qk.w;
+  }
+  const float len = sqrtf(bq.x * bq.x + bq.y * bq.y + bq.z * bq.z + bq.w * bq.w);
+  bq.x /= len; bq.y /= len; bq.z /= len; bq.w /= len;
+  const M3 av = quat_to_rot(bq);
+  sto(model, i, ldo(model, i) * transpose(av));
+  sts(model, i, rotate_sym(av, lds(model, i)));
+  stv(model, P_POS, i, po);
+}
+
+// The triangle list the node publishes for rviz (node/supersurfel_fusion_node.cpp:303-413):
+// per supersurfel a quad of half-extents 3 sqrt(dims) along e1 / e2 as two triangles
+// (p0 p1 p2, p0 p2 p3) and its colour / 255; below the confidence threshold six zero points and
+// a black colour.  The node copies five arrays to the host and loops with OpenMP; here the
+// geometry is produced next to the model.
+__global__ void marker_kernel(SurfelSet set, int n, float conf_thresh, float* __restrict__ points, float* __restrict__ colors) {
+  pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* P = points + (size_t)i * 18;
+  float* C = colors + (size_t)i * 24;
+  if (set.plane(P_CONF)[i] > conf_thresh) {
+    float v0 = 3.0f * sqrtf(set.plane(P_DIM)[i]);
+    float v1 = 3.0f * sqrtf(set.plane(P_DIM + 1)[i]);
+    const V3 e0 = ldv(set, P_ORI, i), e1 = ldv(set, P_ORI + 3, i);
+    V3 pos = ldv(set, P_POS, i);
+    if (!isfinite(v0)) v0 = 0;
+    if (!isfinite(v1)) v1 = 0;
+    if (!isfinite(pos.x) || !isfinite(pos.y) || !isfinite(pos.z)) pos = v3(0.f, 0.f, 0.f);
+    const V3 a = v0 * e0, b = v1 * e1;
+    const V3 p0 = v3(pos.x + a.x + b.x, pos.y + a.y + b.y, pos.z + a.z + b.z);
+    const V3 p1 = v3(pos.x + a.x - b.x, pos.y + a.y - b.y, pos.z + a.z - b.z);
+    const V3 p2 = v3(pos.x - a.x - b.x, pos.y - a.y - b.y, pos.z - a.z - b.z);
+    const V3 p3 = v3(pos.x - a.x + b.x, pos.y - a.y + b.y, pos.z - a.z + b.z);
+    const V3 tri[6] = {p0, p1, p2, p0, p2, p3};
+    const V3 col = ldv(set, P_COL, i);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      P[3 * k] = tri[k].x; P[3 * k + 1] = tri[k].y; P[3 * k + 2] = tri[k].z;
+      C[4 * k] = col.x / 255; C[4 * k + 1] = col.y / 255; C[4 * k + 2] = col.z / 255; C[4 * k + 3] = 1.f;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 18; k++) P[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { C[4 * k] = 0.f; C[4 * k + 1] = 0.f; C[4 * k + 2] = 0.f; C[4 * k + 3] = 1.f; }
+  }
+}
+
 // extractLocalPointCloudKernel (supersurfel_fusion_kernels.cu:490-520); output order is
 // by atomic ticket, as in the reference.
 __global__ void local_cloud_kernel(SurfelSet model, Counters* counters, const DevicePose* pose, float conf_thresh,
@@ -707,6 +825,19 @@ void launch_transform_model(Engine* e, const float* R, const float* t) {
   for (int i = 0; i < 9; i++) tf.R[i] = R[i];
   for (int i = 0; i < 3; i++) tf.t[i] = t[i];
   launch_pdl(e, transform_model_kernel, dim3(cdiv(e->cap, 256)), dim3(256), 0, e->model, e->counters, tf);
+  e->launches++;
+}
+
+void launch_apply_deformation(Engine* e, const float* node_pos, const float* node_rot, const float* node_trans,
+                              const float* weights, const int* nn, int n, int n_nodes) {
+  launch_pdl(e, apply_deformation_kernel, dim3(cdiv(n, 128)), dim3(128), 0, e->model, node_pos, node_rot, node_trans,
+             reinterpret_cast<const float4*>(weights), reinterpret_cast<const int4*>(nn), n, n_nodes);
+  e->launches++;
+}
+
+void launch_markers(Engine* e, bool frame, int n, float conf_thresh, float* points_dev, float* colors_dev) {
+  launch_pdl(e, marker_kernel, dim3(cdiv(n, 128)), dim3(128), 0, frame ? e->frame : e->model, n, conf_thresh, points_dev,
+             colors_dev);
   e->launches++;
 }
 

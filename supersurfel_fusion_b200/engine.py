@@ -71,7 +71,7 @@ EXPORTS = [
     "ssf_set_frame", "ssf_set_segmentation", "ssf_tps_segment", "ssf_get_ransac_samples",
     "ssf_generate_supersurfels", "ssf_icp_system", "ssf_icp_system_enqueue", "ssf_icp", "ssf_icp_begin",
     "ssf_icp_build", "ssf_icp_solve", "ssf_icp_finish", "ssf_peer_handle", "ssf_connect_peers", "ssf_icp_tiled",
-    "ssf_fuse", "ssf_align",
+    "ssf_fuse", "ssf_align", "ssf_apply_deformation", "ssf_get_markers", "ssf_format_tum_pose",
     "ssf_timer_start", "ssf_timer_stop", "ssf_synchronize", "ssf_get_launch_count",
 ]
 
@@ -104,6 +104,10 @@ def load_library():
         lib.ssf_icp_system.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.ssf_icp_system_enqueue.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.ssf_icp.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+        lib.ssf_apply_deformation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_int]
+        lib.ssf_get_markers.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.ssf_format_tum_pose.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t]
         lib.ssf_align.argtypes = [C.c_void_p] + [C.c_void_p, C.c_int] + [C.c_void_p] * 8
         lib.ssf_set_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.ssf_copy_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -520,6 +524,38 @@ class SupersurfelFusion:
                                  C.byref(valid), C.byref(iters), C.byref(pairs), _ptr(sys29))
         self._check(rc, "ssf_align")
         return bool(valid.value), R.reshape(3, 3), t, dict(iters=iters.value, pairs=pairs.value, system=sys29)
+
+    def applyDeformation(self, node_pos, node_rot, node_trans, weights, nn, model_size=None):
+        """DeformationGraph::applyGraphToModel (deformation_graph.cu:840-861): warp the model by an
+        embedded deformation graph supplied by the caller."""
+        node_pos = np.ascontiguousarray(node_pos, np.float32)
+        node_rot = np.ascontiguousarray(node_rot, np.float32)
+        node_trans = np.ascontiguousarray(node_trans, np.float32)
+        weights = np.ascontiguousarray(weights, np.float32)
+        nn = np.ascontiguousarray(nn, np.int32)
+        n = len(weights) if model_size is None else model_size
+        rc = self._lib.ssf_apply_deformation(self._h, _ptr(node_pos), _ptr(node_rot), _ptr(node_trans), len(node_pos),
+                                             _ptr(weights), _ptr(nn), n)
+        self._check(rc, "ssf_apply_deformation")
+
+    def getMarkers(self, which="model", conf_thresh=None):
+        """Triangle-list geometry of publishModelMarker / publishFrameMarker
+        (node/supersurfel_fusion_node.cpp:303-520): (points [n,6,3], colors [n,6,4])."""
+        w = 0 if which == "model" else 1
+        n = self.getCounts()[0] if w == 0 else self.nbSuperpixels
+        thr = self.cfg.conf_thresh if conf_thresh is None else conf_thresh
+        pts = np.zeros((n, 6, 3), np.float32)
+        col = np.zeros((n, 6, 4), np.float32)
+        cnt = C.c_int(0)
+        rc = self._lib.ssf_get_markers(self._h, w, float(thr), _ptr(pts), _ptr(col), n, C.byref(cnt))
+        self._check(rc, "ssf_get_markers")
+        return pts, col
+
+    def formatTumPose(self, timestamp):
+        """One line of the benchmark node's estimated.txt (…rgbd_benchmark_node.cpp:727-729)."""
+        buf = C.create_string_buffer(256)
+        self._check(self._lib.ssf_format_tum_pose(self._h, str(timestamp).encode(), buf, 256), "ssf_format_tum_pose")
+        return buf.value.decode()
 
     def fuse(self):
         self._check(self._lib.ssf_fuse(self._h), "ssf_fuse")
