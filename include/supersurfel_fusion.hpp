@@ -77,15 +77,27 @@ class SupersurfelFusion {
   }
 
   // processFrame(const cv::Mat& rgb_h /*8UC3 RGB*/, const cv::Mat& depth_h /*32FC1 m*/)
-  void processFrame(const ImageView& rgb_h, const ImageView& depth_h, const Transform3* pose_prior = nullptr) {
+  // filter_depth = true runs the reference's cv::cuda::bilateralFilter(depth, depth, -1, 0.03, 4.5)
+  // (supersurfel_fusion.cu:180) inside the library; false expects an already filtered image.
+  void processFrame(const ImageView& rgb_h, const ImageView& depth_h, const Transform3* pose_prior = nullptr,
+                    bool filter_depth = true) {
     float prior[12];
-    if (pose_prior) {
-      for (int i = 0; i < 9; i++) prior[i] = pose_prior->R.rows[i / 3][i % 3];
-      for (int i = 0; i < 3; i++) prior[9 + i] = pose_prior->t[i];
-    }
+    pack(pose_prior, prior);
     check(ssf_process_frame(h_, static_cast<const uint8_t*>(rgb_h.data), rgb_h.step,
-                            static_cast<const float*>(depth_h.data), depth_h.step, pose_prior ? prior : nullptr, 0),
+                            static_cast<const float*>(depth_h.data), depth_h.step, pose_prior ? prior : nullptr,
+                            filter_depth ? SSF_FLAG_BILATERAL : 0u),
           "ssf_process_frame");
+  }
+  // the 16-bit depth image the nodes receive, decoded on the device
+  // (depth.convertTo(CV_32FC1, depth_scale), node/supersurfel_fusion_rgbd_benchmark_node.cpp:609-610)
+  void processFrame(const ImageView& rgb_h, const ImageView& depth16_h, float depth_scale,
+                    const Transform3* pose_prior = nullptr, bool filter_depth = true) {
+    float prior[12];
+    pack(pose_prior, prior);
+    check(ssf_process_frame_depth16(h_, static_cast<const uint8_t*>(rgb_h.data), rgb_h.step,
+                                    static_cast<const uint16_t*>(depth16_h.data), depth16_h.step, depth_scale,
+                                    pose_prior ? prior : nullptr, filter_depth ? SSF_FLAG_BILATERAL : 0u),
+          "ssf_process_frame_depth16");
   }
   void generateSupersurfels() { check(ssf_generate_supersurfels(h_), "ssf_generate_supersurfels"); }
   void exportModel(const std::string& filename) { check(ssf_export_model(h_, filename.c_str()), "ssf_export_model"); }
@@ -136,6 +148,42 @@ class SupersurfelFusion {
     positions.resize(3 * (size_t)n);
     normals.resize(3 * (size_t)n);
   }
+  // DenseRegistration::align (dense_registration.hpp:44-59) as closeGlobalLoop uses it
+  // (supersurfel_fusion.cu:776-792): keyframe supersurfels -> current frame
+  bool align(SupersurfelsHost& keyframe, const Transform3& init, Transform3& result) {
+    SsfSurfels v = keyframe.view();
+    int valid = 0;
+    check(ssf_align(h_, &v, (int)keyframe.size(), &init.R.rows[0][0], init.t, &result.R.rows[0][0], result.t, &valid,
+                    nullptr, nullptr, nullptr),
+          "ssf_align");
+    return valid != 0;
+  }
+  // DeformationGraph::applyGraphToModel (deformation_graph.cu:840-861)
+  void applyDeformation(const std::vector<float>& nodes_positions, const std::vector<float>& nodes_rotations,
+                        const std::vector<float>& nodes_translations, const std::vector<float>& neighbours_weights,
+                        const std::vector<int32_t>& neighbours_idx) {
+    check(ssf_apply_deformation(h_, nodes_positions.data(), nodes_rotations.data(), nodes_translations.data(),
+                                (int)(nodes_positions.size() / 3), neighbours_weights.data(), neighbours_idx.data(),
+                                (int)(neighbours_weights.size() / 4)),
+          "ssf_apply_deformation");
+  }
+  // what publishModelMarker / publishFrameMarker build on the host (supersurfel_fusion_node.cpp:303-520)
+  void getMarkers(bool frame, std::vector<float>& points, std::vector<float>& colors) {
+    int n = 0;
+    if (frame) check(ssf_get_nb_superpixels(h_, &n), "ssf_get_nb_superpixels");
+    else n = getnbSupersurfels();
+    points.resize(18 * (size_t)n);
+    colors.resize(24 * (size_t)n);
+    if (n == 0) return;
+    check(ssf_get_markers(h_, frame ? 1 : 0, frame ? 0.0f : cfg_.conf_thresh, points.data(), colors.data(), n, nullptr),
+          "ssf_get_markers");
+  }
+  // one line of estimated.txt (supersurfel_fusion_rgbd_benchmark_node.cpp:727-729)
+  std::string tumPoseLine(const std::string& timestamp) {
+    char line[256];
+    check(ssf_format_tum_pose(h_, timestamp.c_str(), line, sizeof(line)), "ssf_format_tum_pose");
+    return std::string(line);
+  }
   SsfFrameStats getFrameStats() {
     SsfFrameStats st;
     check(ssf_get_frame_stats(h_, &st), "ssf_get_frame_stats");
@@ -144,6 +192,11 @@ class SupersurfelFusion {
   SsfHandle handle() { return h_; }
 
  private:
+  static void pack(const Transform3* tf, float* prior) {
+    if (!tf) return;
+    for (int i = 0; i < 9; i++) prior[i] = tf->R.rows[i / 3][i % 3];
+    for (int i = 0; i < 3; i++) prior[9 + i] = tf->t[i];
+  }
   void check(int rc, const char* what) {
     if (rc != SSF_OK) throw std::runtime_error(std::string(what) + " failed: " + (h_ ? ssf_last_error(h_) : "no handle"));
   }
