@@ -84,9 +84,12 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+SIZE = [640, 480]   # --size WxH: 640x480 is the metric's configuration (configs[1]); 1280x960 is configs[2]
+
+
 def render_frames(seed):
     from supersurfel_fusion_b200.synth import SyntheticSequence
-    seq = SyntheticSequence(width=640, height=480, seed=seed)
+    seq = SyntheticSequence(width=SIZE[0], height=SIZE[1], seed=seed)
     frames = [seq.frame(k) for k in range(N_UNIQUE_FRAMES)]
     return seq, frames
 
@@ -339,15 +342,15 @@ def run_ours(args, rank, world, local_rank):
     value = total_frames / (ms * 1e-3)
     e2e = total_frames / (ms_e * 1e-3)
     line = {
-        "metric": "RGB-D frames/sec @640x480", "value": value, "unit": "frames/s", "n_gpus": world,
+        "metric": "RGB-D frames/sec @%dx%d" % tuple(SIZE), "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD if world == 1 else "configs[3]: %d independent 640x480 synthetic sequences, one per GPU, no NCCL on the data path" % world,
+        "config": {"workload": (WORKLOAD if SIZE == [640, 480] else "configs[2]: %dx%d synthetic RGB-D stream, full pipeline" % tuple(SIZE)) if world == 1 else "configs[3]: %d independent %dx%d synthetic sequences, one per GPU, no NCCL on the data path" % (world, SIZE[0], SIZE[1]),
                    "params": "launch/supersurfel_fusion_rgbd_benchmark.launch", "frames_per_gpu": args.steps,
                    "l2_policy": "per-frame working set (~9 MB images + model) is L2 resident by nature of the workload; "
                                 "the roofline kernel streams 604 MB per launch (> 126 MB L2), no flush needed",
                    "timing": "CUDA events on the engine stream, max over ranks"},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": 640 * 480 * 7, "d2h_bytes_per_step": 104,
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": SIZE[0] * SIZE[1] * 7, "d2h_bytes_per_step": 104,
                 "ms_per_step": ms_e / args.steps, "wall_ms_per_step": wall_e / args.steps},
         "wall_ms_per_step": wall_ms / args.steps,
         "gpu_launches": int(launches),
@@ -368,6 +371,7 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", default="640x480", help="frame size WxH (default: the metric's 640x480; 1280x960 = configs[2])")
     ap.add_argument("--skip-extras", action="store_true", help="frames only: no roofline / cpu_baseline legs (for ncu)")
     ap.add_argument("--roofline-only", action="store_true", help="only the ICP roofline leg (for ncu --set full)")
     args = ap.parse_args()
@@ -376,6 +380,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.warmup < 3:
         args.warmup = 3
+    SIZE[0], SIZE[1] = (int(v) for v in args.size.lower().split("x"))
     if args.roofline_only:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         print(json.dumps(icp_roofline(local_rank, peaks)))

@@ -849,9 +849,9 @@ int ssf_connect_peers(SsfHandle h, int rank, int world, const void* handles) {
     ptrs[g] = static_cast<float*>(p);
   }
   SSF_CUDA(e, cudaMemcpy(e->xpeers_dev, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice));
-  SSF_CUDA(e, cudaMemset(e->xbuf, 0, sizeof(float) * 2 * SSF_MAX_PEERS * 64));
-  unsigned int zero = 0;
-  SSF_CUDA(e, cudaMemcpy(&e->icp->xseq, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+  // The exchange buffer and the sequence counter are zero from ssf_create and must NOT be
+  // cleared here: a peer that connected earlier may already have stored its first slot and
+  // flag into this rank's buffer (clearing it made the first exchange hang, intermittently).
   e->xrank = rank;
   e->xworld = world;
   return SSF_OK;

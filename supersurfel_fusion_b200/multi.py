@@ -95,6 +95,7 @@ def connect_peers(engine, dist, device=None):
     dist.all_gather(parts, mine)
     handles = np.concatenate([p.cpu().numpy() for p in parts])
     engine.connectPeers(rank, world, handles)
+    dist.barrier()      # every rank has mapped every buffer before anyone starts a fused loop
 
 
 def fused_tile_parallel_icp(engine, dist, n_visible, R_init=None, t_init=None):

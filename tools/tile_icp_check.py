@@ -23,6 +23,12 @@ from supersurfel_fusion_b200.engine import SsfSurfels, _ptr  # noqa: E402
 from supersurfel_fusion_b200.synth import synthetic_icp_problem  # noqa: E402
 
 
+def note(msg):
+    if os.environ.get("SSF_VERBOSE"):
+        with open(os.path.join(ROOT, "gpurun_out", "tile_dbg_rank%s.log" % os.environ.get("RANK", "0")), "a") as f:
+            f.write("%.3f %s\n" % (time.time(), msg))
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2 * 1024 * 1024
     rank = int(os.environ.get("RANK", "0"))
@@ -43,14 +49,17 @@ def main():
     R = np.eye(3, dtype=np.float32)
     t = np.array([0.004, -0.003, 0.005], np.float32)
     # single GPU, whole loop on the device
+    note("engine ready")
     ok1, R1, t1, st1 = eng.icp(R, t)
     torch.cuda.synchronize()
+    note("single done iters=%d" % st1["iters"])
     t0 = time.perf_counter()
     for _ in range(5):
         eng.icp(R, t)
     one_ms = (time.perf_counter() - t0) / 5 * 1e3
     # tiled across the ranks
     okN, RN, tN, stN = multi.tile_parallel_icp(eng, dist if world > 1 else None, n, R, t, device=dev)
+    note("nccl-tiled done iters=%d" % stN["iters"])
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -61,7 +70,9 @@ def main():
     fused = {}
     if world > 1:
         multi.connect_peers(eng, dist, device=dev)
+        note("peers connected")
         okF, RF, tF, stF = multi.fused_tile_parallel_icp(eng, dist, n, R, t)
+        note("fused done iters=%d" % stF["iters"])
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
