@@ -135,7 +135,27 @@ def time_cpu_oracle(frames, cam, n_frames, threads=1, warmup=0):
     return threads * n_frames / dt, dt
 
 
+class _StdoutToStderr:
+    """The reference's own code prints to stdout (CachedAllocator::free_all, cached_allocator.cpp);
+    keep this process' stdout to the ONE JSON line by pointing fd 1 at stderr while it runs."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 def time_reference_gpu_kernels(frames, cam, n_frames):
+    with _StdoutToStderr():
+        return _time_reference_gpu_kernels(frames, cam, n_frames)
+
+
+def _time_reference_gpu_kernels(frames, cam, n_frames):
     """The reference's OWN CUDA kernels (TPS_RGBD, DenseRegistration and the surfel kernels,
     compiled unmodified for sm_100a into oracle/_ref/libssf_ref.so) replaying processFrame on
     this GPU: context for the speed-up, next to the CPU arm the contract asks for."""
