@@ -217,9 +217,9 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   e->icp_stages = icp_configure(e->icp_stages);
   e->tps_grid = tps_persistent_grid(device, e->gx, e->gy, cfg->cell_size, e->H, cfg->seg_iter, &e->tps_cache_slots);
   // The one-kernel (cooperative, band-owned) form of the segmentation is kept as an option:
-  // measured on B200 at VGA it is ~8 % slower per frame than the graph of small kernels
-  // (per pass: ~1.2 us cache fill + ~4 us relabel + ~1.2 us barrier vs ~7 us for two graph
-  // nodes), see DESIGN.md section 7.
+  // measured on B200 at VGA it is ~6 % slower per frame than the graph of small kernels
+  // (0.602 vs 0.559 ms; per pass ~1.4 us cache fill + ~3.7 us relabel + ~1.7 us barrier for the
+  // colour passes, 3.2 + 4.1 + 2.4 us with the disparity plane), see DESIGN.md section 3.
   e->tps_persistent = 0;
   if (const char* v = getenv("SSF_TPS_PERSISTENT")) e->tps_persistent = (atoi(v) != 0 && e->tps_grid > 0) ? 1 : 0;
   e->icp_debug = 0;

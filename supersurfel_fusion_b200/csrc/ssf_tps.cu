@@ -429,92 +429,6 @@ __global__ void __launch_bounds__(128) tps_pass_kernel(TpsArgs a, int OX, int OY
   tps_pass_item<DISP>(a, src, q, ry, OX, OY);
 }
 
-// One lane per active pixel (the persistent kernel's form of a pass): the two pixels of an
-// adjacent pair sit in neighbouring lanes and exchange what the pair-per-thread form keeps
-// in registers (the partner's validity and the boundary delta meant for it) by shuffles.
-// Every lane of the warp must call this; out-of-range lanes pass in_range = false.
-template <bool DISP, typename SP>
-__device__ __forceinline__ void tps_pass_pixel(const TpsArgs& a, const SP& spsrc, int q, int j, int ry, int OX,
-                                               int OY, bool in_range) {
-  const int y = 2 * ry + OY;
-  const int rx = (OX ? 2 * q : 2 * q - 1) + j;
-  const int x = 2 * rx + ((rx + OX) & 1);
-  const bool ok = in_range && ry < a.raw_h && y < a.H && 32 * (ry / 16) + OY < a.H && rx >= 0 && rx < a.raw_w &&
-                  32 * (rx / 16) < a.W && x < a.W;
-  int L[3][4];
-  Decision d;
-  PixelIn pin;
-  pin.col = make_uchar4(0, 0, 0, 0);
-  float dv = 0.f;
-  d.index = d.new_index = -1; d.b = 0; d.inlier = d.prev_inlier = 0;
-  if (ok) {
-#pragma unroll
-    for (int r = 0; r < 3; r++) {
-      const int yy = y - 1 + r;
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        const int xx = x - 1 + c;
-        L[r][c] = (xx >= 0 && xx < a.W && yy >= 0 && yy < a.H) ? a.labels[(size_t)yy * a.W + xx] : -1;
-      }
-      L[r][3] = -1;
-    }
-    pin = tps_fetch_pixel<DISP>(a, (size_t)y * a.W + x);
-    if (a.debug != 2) tps_decide<DISP>(a, spsrc, pin, x, y, L, 1, d, dv);
-  }
-  // all pass-start reads of the warp are done before any lane writes
-  __syncwarp();
-  const bool partner_ok = __shfl_xor_sync(0xffffffffu, ok ? 1 : 0, 1) != 0;
-  const bool moved = ok && d.new_index != d.index && a.debug != 1;
-  const size_t p = ok ? (size_t)y * a.W + x : 0;
-  int to_partner = 0;
-  if (moved) {
-    const int nxs[4] = {0, -1, 1, 0}, nys[4] = {-1, 0, 0, 1};
-    const int nl[4] = {L[0][1], L[1][0], L[1][2], L[2][1]};
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int i_n = nl[k];
-      int delta = 0;
-      if (i_n == d.new_index) delta = -1;
-      else if (i_n == d.index) delta = 1;
-      if (delta == 0 || i_n == -1) continue;
-      const bool is_partner = partner_ok && ((j == 0 && k == 2) || (j == 1 && k == 1));
-      if (is_partner) to_partner += delta;
-      else atomicAdd(&a.bound[(size_t)(y + nys[k]) * a.W + (x + nxs[k])], delta);
-    }
-    const uchar4 col = pin.col;
-    SpSums* o = &a.sums[d.index];
-    SpSums* n = &a.sums[d.new_index];
-    add64(&o->x, -x); add64(&o->y, -y); add64(&o->r, -(int)col.x); add64(&o->g, -(int)col.y);
-    add64(&o->b, -(int)col.z); add64(&o->n, -1);
-    add64(&n->x, x); add64(&n->y, y); add64(&n->r, col.x); add64(&n->g, col.y); add64(&n->b, col.z);
-    add64(&n->n, 1);
-    a.labels[p] = d.new_index;
-  }
-  if (DISP && ok && a.debug != 1) {
-    const unsigned char inl = d.inlier, pin = d.prev_inlier;
-    if (inl && (!pin || moved)) {
-      SpSums* s = &a.sums[d.new_index];
-      const long long qd = quantize(dv, kDispFix, kDispClamp);
-      add64(&s->dx, x); add64(&s->dy, y); add64(&s->dxx, (long long)x * x); add64(&s->dyy, (long long)y * y);
-      add64(&s->dxy, (long long)x * y); add64(&s->dxd, (long long)x * qd); add64(&s->dyd, (long long)y * qd);
-      add64(&s->dd, qd); add64(&s->dn, 1);
-    }
-    if (pin && (!inl || moved)) {
-      SpSums* s = &a.sums[d.index];
-      const long long qd = quantize(dv, kDispFix, kDispClamp);
-      add64(&s->dx, -x); add64(&s->dy, -y); add64(&s->dxx, -(long long)x * x); add64(&s->dyy, -(long long)y * y);
-      add64(&s->dxy, -(long long)x * y); add64(&s->dxd, -(long long)x * qd); add64(&s->dyd, -(long long)y * qd);
-      add64(&s->dd, -qd); add64(&s->dn, -1);
-    }
-    if (inl != pin) a.inliers[p] = inl;
-  }
-  const int from_partner = __shfl_xor_sync(0xffffffffu, to_partner, 1);
-  if (ok) {
-    if (moved) a.bound[p] = d.b;                              // own "= b" wins
-    else if (from_partner != 0) a.bound[p] += from_partner;   // only the pair touches it
-  }
-}
-
 // ---- RANSAC plane initialisation (TPS_RGBD_kernels.cu:318-467, 112-190) --------------
 __global__ void tps_rng_init_kernel(curandState* states, int n) {
   pdl_sync();
@@ -789,7 +703,10 @@ struct TpsRun {
   unsigned long long* trace;   // optional per-CTA phase timestamps (profiling aid), else NULL
 };
 
-constexpr int TPS_PERSIST_THREADS = 512;
+// 768 threads: at VGA a CTA's share of a pass (77 040 adjacent-pixel pairs / 148 CTAs = 521) is
+// ONE round of one thread per pair -- one dependent chain of L2 round trips per pass instead of
+// the three rounds a 512-thread, lane-per-pixel CTA needed
+constexpr int TPS_PERSIST_THREADS = 768;
 
 // Grid-wide barrier for the co-resident CTAs of the persistent kernel: one release
 // atomic per CTA on a monotonically increasing ticket and an acquire spin by thread 0
@@ -833,7 +750,7 @@ struct TpsTrace {
 };
 
 struct TpsBand {
-  int ry0, ry1;        // active-row range [ry0, ry1) of this CTA (row y = 2*ry + OY)
+  int i0, i1;          // pair range [i0, i1) of this CTA; pair i = (active row i / pairs, pair i % pairs)
   int first, count;    // cached superpixel ids
 };
 
@@ -847,12 +764,8 @@ __device__ __forceinline__ void tps_phase_pass(const TpsArgs& a, GridBarrier& gr
   tr.stamp();
   const SpCached<DISP> src = {cache, a.sums, band.first, band.count};
   const int pairs = a.raw_w / 2 + 1;
-  const int items = 2 * pairs * (band.ry1 - band.ry0);     // one lane per pixel, partners adjacent
-  for (int base = 0; base < items; base += blockDim.x) {
-    const int i = base + threadIdx.x;
-    const int pr = i >> 1;
-    tps_pass_pixel<DISP>(a, src, pr % pairs, i & 1, band.ry0 + pr / pairs, OX, OY, i < items);
-  }
+  for (int i = band.i0 + threadIdx.x; i < band.i1; i += blockDim.x)     // one thread per adjacent pair
+    tps_pass_item<DISP>(a, src, i % pairs, i / pairs, OX, OY);
   __syncthreads();
   tr.stamp();
   grid.sync();
@@ -880,16 +793,19 @@ __global__ void __launch_bounds__(TPS_PERSIST_THREADS, 1) tps_persistent_kernel(
   TpsTrace tr = {r.trace, 0};
   TpsBand band;
   {
-    const int per = (a.raw_h + gridDim.x - 1) / gridDim.x;
-    band.ry0 = min(a.raw_h, (int)blockIdx.x * per);
-    band.ry1 = min(a.raw_h, band.ry0 + per);
-    const int y0 = 2 * band.ry0, y1 = min(a.H - 1, 2 * band.ry1 + 1);
+    const int pairs = a.raw_w / 2 + 1;
+    const int total = pairs * a.raw_h;
+    const int per = (total + gridDim.x - 1) / gridDim.x;
+    band.i0 = min(total, (int)blockIdx.x * per);
+    band.i1 = min(total, band.i0 + per);
+    const int ry0 = band.i0 / pairs, ry1 = (band.i1 > band.i0) ? (band.i1 - 1) / pairs + 1 : ry0;
+    const int y0 = 2 * ry0, y1 = min(a.H - 1, 2 * ry1 + 1);
     // A boundary moves at most one pixel per pass, so after all 4*nb_iters passes a pixel's
     // label was seeded at most `margin` grid-cell rows away: the cache always hits.
     const int margin = (4 * r.nb_iters + 1 + a.cell - 1) / a.cell;
     const int c0 = max(0, y0 / a.cell - margin), c1 = min(a.gy - 1, y1 / a.cell + margin);
     band.first = c0 * a.gx;
-    band.count = (band.ry1 > band.ry0) ? min(r.cache_slots, (c1 - c0 + 1) * a.gx) : 0;
+    band.count = (band.i1 > band.i0) ? min(r.cache_slots, (c1 - c0 + 1) * a.gx) : 0;
   }
   // pass order per iteration: (0,0) (1,1) (0,1) (1,0) (TPS_RGBD.cu:190-272).  One copy of the
   // pass body per phase (not eight): the kernel must stay inside the instruction cache.
@@ -972,7 +888,7 @@ int tps_persistent_grid(int device, int gx, int gy, int cell, int height, int nb
   if (!coop) return 0;
   // rows of grid cells a band of ceil(H/2/sms) active rows touches, plus two on each side
   const int raw_h = 16 * ((height / 2 + 15) / 16);
-  const int per = (raw_h + sms - 1) / sms;
+  const int per = (raw_h + sms - 1) / sms + 1;      // a CTA's pair range may straddle one more active row
   const int margin = (4 * nb_iters + 1 + cell - 1) / cell;
   int rows = (2 * per + 1) / cell + 2 + 2 * margin;
   if (rows > gy) rows = gy;
