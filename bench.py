@@ -10,10 +10,12 @@ sequences (configs[3]), one process and one engine per GPU, no data-path collect
 ("weak" scaling); the only collectives are the timing barrier and the max-over-ranks.
 
 Rank 0 prints ONE JSON line:
-  value     frames/s with the frames already resident in HBM (ssf_process_frame_device)
-  e2e       frames/s through the C-ABI call a reference user makes (ssf_process_frame) with
-            pinned HOST buffers: the H2D copy of the frame and the D2H read of the
-            pose/stats are inside the timed region
+  value     frames/s with the frames already resident in HBM
+  e2e       frames/s through the C-ABI with pinned HOST buffers: the H2D copy of the frame and
+            the D2H read of the pose/stats are inside the timed region
+            (both through ssf_submit_frame / ssf_wait_frame, two frames in flight; the numbers
+            of the synchronous ssf_process_frame, the reference's call shape, are reported
+            under "synchronous"; --no-pipeline times only those)
   roofline  the ICP system kernel (the metric kernel) at HBM-bound sizing: 16 Mi source
             supersurfels vs a 2560x1920 frame, algorithmic 72 B per supersurfel
   cpu_baseline  the CPU oracle port of the same path on this box's host cores, bounded sample
@@ -307,16 +309,35 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(tns, op=dist.ReduceOp.MAX)
         return float(tns.item())
 
-    def timed(run_step, steps, warmup):
+    def timed(bufs, device_resident, pipelined, steps, warmup):
+        """K frames through the engine after W warm-up frames; CUDA events on the engine's stream around the
+        timed region (the pipeline is drained inside it), max over ranks.  pipelined: ssf_submit_frame /
+        ssf_wait_frame, the segmentation of frame k+1 overlapping the tracking of frame k (two frames in
+        flight, results identical to the synchronous call, tests/test_gpu_engine.py)."""
         eng = SupersurfelFusion(dev).initialize(CamParam(*cam), **PARAMS)
+
+        def sync_step(s):
+            k = frame_index(s)
+            if device_resident:
+                eng.processFrameDevice(*bufs[k])
+            else:
+                eng.processFrame(*bufs[k])
+
         for s in range(warmup):
-            run_step(eng, s)
+            sync_step(s)
         barrier()
         l0 = eng.launchCount()
         eng.timerStart()                      # CUDA event on the engine's stream
         w0 = time.perf_counter()
-        for s in range(warmup, warmup + steps):
-            run_step(eng, s)
+        if pipelined:
+            eng.submitFrame(*bufs[frame_index(warmup)])
+            for s in range(warmup + 1, warmup + steps):
+                eng.submitFrame(*bufs[frame_index(s)])
+                eng.waitFrame()
+            eng.waitFrame()
+        else:
+            for s in range(warmup, warmup + steps):
+                sync_step(s)
         ms = eng.timerStop()                  # records + synchronises
         wall = (time.perf_counter() - w0) * 1e3
         barrier()
@@ -324,14 +345,6 @@ def run_ours(args, rank, world, local_rank):
         stats = eng.getFrameStats()
         eng.close()
         return max_over_ranks(ms), max_over_ranks(wall), launches, stats
-
-    def step_resident(eng, s):
-        k = frame_index(s)
-        eng.processFrameDevice(d_rgb[k], d_dep[k])
-
-    def step_e2e(eng, s):
-        k = frame_index(s)
-        eng.processFrame(h_rgb[k], h_dep[k])
 
     def multi_stream(k, steps):
         """Throughput headroom of ONE GPU: k independent sequences, one engine (own stream, own CUDA
@@ -366,8 +379,15 @@ def run_ours(args, rank, world, local_rank):
 
     sampler = ClockSampler(dev)
     sampler.start()
-    ms, wall_ms, launches, stats = timed(step_resident, args.steps, args.warmup)
-    ms_e, wall_e, _, _ = timed(step_e2e, args.steps, args.warmup)
+    dev_bufs = list(zip(d_rgb, d_dep))
+    host_bufs = list(zip(h_rgb, h_dep))
+    pipelined = not args.no_pipeline
+    ms, wall_ms, launches, stats = timed(dev_bufs, True, pipelined, args.steps, args.warmup)
+    ms_e, wall_e, _, _ = timed(host_bufs, False, pipelined, args.steps, args.warmup)
+    sync_ms = sync_ms_e = None
+    if pipelined and not args.skip_extras:
+        sync_ms = timed(dev_bufs, True, False, args.steps, args.warmup)[0]
+        sync_ms_e = timed(host_bufs, False, False, args.steps, args.warmup)[0]
     clocks = sampler.stop()
 
     if rank != 0:
@@ -404,10 +424,17 @@ def run_ours(args, rank, world, local_rank):
                    "params": "launch/supersurfel_fusion_rgbd_benchmark.launch", "frames_per_gpu": args.steps,
                    "l2_policy": "per-frame working set (~9 MB images + model) is L2 resident by nature of the workload; "
                                 "the roofline kernel streams 604 MB per launch (> 126 MB L2), no flush needed",
-                   "timing": "CUDA events on the engine stream, max over ranks"},
+                   "pipeline": ("ssf_submit_frame / ssf_wait_frame: two frames in flight, segmentation of frame k+1 overlaps "
+                                "registration + fusion of frame k on a second stream; identical results to the "
+                                "synchronous ssf_process_frame, whose numbers are under 'synchronous'") if pipelined
+                               else "synchronous ssf_process_frame, one frame at a time",
+                   "timing": "CUDA events on the engine stream around all K frames (pipeline drained inside), max over ranks"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": SIZE[0] * SIZE[1] * 7, "d2h_bytes_per_step": 104,
                 "ms_per_step": ms_e / args.steps, "wall_ms_per_step": wall_e / args.steps},
         "wall_ms_per_step": wall_ms / args.steps,
+        "synchronous": None if sync_ms is None else {
+            "value": total_frames / (sync_ms * 1e-3), "e2e": total_frames / (sync_ms_e * 1e-3), "unit": "frames/s",
+            "ms_per_frame": sync_ms / args.steps, "what": "one ssf_process_frame call per frame (the reference's call shape)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
@@ -428,6 +455,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default="640x480", help="frame size WxH (default: the metric's 640x480; 1280x960 = configs[2])")
+    ap.add_argument("--no-pipeline", action="store_true", help="time the synchronous ssf_process_frame instead of submit/wait")
     ap.add_argument("--skip-extras", action="store_true", help="frames only: no roofline / cpu_baseline legs (for ncu)")
     ap.add_argument("--roofline-only", action="store_true", help="only the ICP roofline leg (for ncu --set full)")
     args = ap.parse_args()

@@ -143,6 +143,17 @@ int ssf_process_frame_depth16(SsfHandle h, const uint8_t* rgb, size_t rgb_stride
 int ssf_process_frame_device(SsfHandle h, const uint8_t* rgb_dev, const float* depth_dev,
                              const float* pose_prior_Rt12, uint32_t flags);
 int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out);
+/* Pipelined form of processFrame for streams of frames: ssf_submit_frame() enqueues a frame and
+ * returns at once, ssf_wait_frame() blocks until the OLDEST submitted frame is done and returns
+ * its stats and pose.  Up to two frames may be in flight: the segmentation + extraction of frame
+ * k+1 (which depend only on its images) overlap the registration + fusion of frame k on a second
+ * stream.  Same kernels, same order per stage: results are identical to ssf_process_frame; the
+ * input buffers must stay valid until the frame has been waited for (pinned host memory or
+ * device memory for a truly asynchronous copy).  The synchronous entry points and the getters
+ * require that no frame is in flight. */
+int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth,
+                     size_t depth_stride, const float* pose_prior_Rt12, uint32_t flags);
+int ssf_wait_frame(SsfHandle h, SsfFrameStats* out, float R[9], float t[3]);
 
 /* ---- ingest (supersurfel_fusion.cu:171-181) -------------------------------- */
 /* cv::cuda::bilateralFilter(depth, depth, kernel_size, sigma_color, sigma_spatial)

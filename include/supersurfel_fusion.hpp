@@ -99,6 +99,22 @@ class SupersurfelFusion {
                                     pose_prior ? prior : nullptr, filter_depth ? SSF_FLAG_BILATERAL : 0u),
           "ssf_process_frame_depth16");
   }
+  // Pipelined processFrame for streams: submit frame k+1 before waiting for frame k; the
+  // segmentation of the newer frame overlaps the registration + fusion of the older one.
+  void submitFrame(const ImageView& rgb_h, const ImageView& depth_h, const Transform3* pose_prior = nullptr,
+                   bool filter_depth = true) {
+    float prior[12];
+    pack(pose_prior, prior);
+    check(ssf_submit_frame(h_, static_cast<const uint8_t*>(rgb_h.data), rgb_h.step,
+                           static_cast<const float*>(depth_h.data), depth_h.step, pose_prior ? prior : nullptr,
+                           filter_depth ? SSF_FLAG_BILATERAL : 0u),
+          "ssf_submit_frame");
+  }
+  Transform3 waitFrame(SsfFrameStats* stats = nullptr) {
+    Transform3 tf;
+    check(ssf_wait_frame(h_, stats, &tf.R.rows[0][0], tf.t), "ssf_wait_frame");
+    return tf;
+  }
   void generateSupersurfels() { check(ssf_generate_supersurfels(h_), "ssf_generate_supersurfels"); }
   void exportModel(const std::string& filename) { check(ssf_export_model(h_, filename.c_str()), "ssf_export_model"); }
   void computeSuperpixelSegIm(std::vector<uint8_t>& seg_im_bgr) {

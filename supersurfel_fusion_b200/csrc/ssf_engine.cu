@@ -39,7 +39,14 @@ __global__ void frame_end_kernel(Counters* counters, const DevicePose* pose, con
   rep->icp_iters = icp->active ? icp->iter : 0;
   rep->icp_inliers = icp->active ? icp->inliers : 0.0f;
   rep->icp_error = icp->active ? icp->error : 0.0;
-  if (advance) counters->stamp += 1;   // supersurfel_fusion.cu:521
+  if (advance & 1) counters->stamp += 1;                  // supersurfel_fusion.cu:521
+  if (advance & 2) counters->seg_stamp = counters->stamp; // synchronous mode: the two stamps move together
+}
+
+// end of the segmentation stage of the pipelined mode: the next frame to be segmented is stamp + 1
+__global__ void seg_end_kernel(Counters* counters) {
+  pdl_sync();
+  counters->seg_stamp += 1;
 }
 
 __global__ void split_lmap_kernel(const int2* lmap, float* slanted, size_t n) {
@@ -49,6 +56,21 @@ __global__ void split_lmap_kernel(const int2* lmap, float* slanted, size_t n) {
 }
 
 struct EngineImpl : public SsfEngine {
+  // pipelined mode (ssf_submit_frame / ssf_wait_frame): per slot, a segmentation graph per ingest
+  // variant on `stream`, a tracking graph on `stream2`, their events, report and prior buffers
+  cudaGraphExec_t seg_graph[2][2];
+  bool seg_ready[2][2];
+  uint64_t seg_launches[2][2];
+  cudaGraphExec_t track_graph[2];
+  bool track_ready[2];
+  uint64_t track_launches[2];
+  cudaEvent_t ev_seg[2], ev_done[2], ev_t0[2], ev_t1[2];
+  FrameReport* d_report2[2];
+  FrameReport* h_report2[2];
+  float* h_prior2[2];
+  int pipe_next;     // slot of the next submitted frame
+  int pipe_oldest;   // slot of the oldest frame in flight
+  int in_flight;
   uint64_t launches_per_frame[2];
   FrameReport* d_report;
   FrameReport* h_report;
@@ -72,7 +94,18 @@ static cudaError_t dalloc(T** p, size_t count) {
 static const int kBilateralKernel = -1;
 static const float kBilateralSigmaColor = 0.03f, kBilateralSigmaSpatial = 4.5f;
 
-static void enqueue_frame(EngineImpl* e, bool bilateral) {
+// point the engine at one of the two frame hand-over sets
+static void select_slot(EngineImpl* e, int s) {
+  e->cur_slot = s;
+  e->lmap = e->slot[s].lmap;
+  e->frame = e->slot[s].frame;
+  e->ftab = e->slot[s].ftab;
+  e->matched = e->slot[s].matched;
+  e->best = e->slot[s].best;
+}
+
+// stage 1: ingest + segmentation + extraction (reads the inputs, writes the selected FrameOut)
+static void enqueue_seg(EngineImpl* e, bool bilateral) {
   const float* depth = e->in_depth;
   if (bilateral) {
     launch_bilateral(e, e->in_depth, e->depth_f, kBilateralKernel, kBilateralSigmaColor, kBilateralSigmaSpatial);
@@ -81,12 +114,21 @@ static void enqueue_frame(EngineImpl* e, bool bilateral) {
   launch_ingest(e, e->in_rgb, (size_t)e->W * 3, depth, (size_t)e->W * 4);
   launch_tps(e);
   launch_extract(e);
+}
+
+// stage 2: registration + fusion (reads the selected FrameOut, owns pose / model / counters)
+static void enqueue_track(EngineImpl* e, FrameReport* report, int advance) {
   launch_icp_begin_from_pose(e);
   launch_icp_loop(e);
   launch_icp_finish(e, true);
   launch_fuse(e);
-  launch_pdl(e, frame_end_kernel, dim3(1), dim3(1), 0, e->counters, e->pose, e->icp, e->d_report, 1);
+  launch_pdl(e, frame_end_kernel, dim3(1), dim3(1), 0, e->counters, e->pose, e->icp, report, advance);
   e->launches++;
+}
+
+static void enqueue_frame(EngineImpl* e, bool bilateral) {
+  enqueue_seg(e, bilateral);
+  enqueue_track(e, e->d_report, 3);
 }
 
 static int ensure_scratch(EngineImpl* e, size_t bytes) {
@@ -125,6 +167,7 @@ static int copy_members(EngineImpl* e, const SsfSurfels& dst, const SsfSurfels& 
 }
 
 static int read_report(EngineImpl* e, bool advance) {
+  if (e->in_flight) { e->err = "pipelined frames in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
   launch_pdl(e, frame_end_kernel, dim3(1), dim3(1), 0, e->counters, e->pose, e->icp, e->d_report, advance ? 1 : 0);
   e->launches++;
   SSF_CUDA(e, cudaMemcpyAsync(e->h_report, e->d_report, sizeof(FrameReport), cudaMemcpyDeviceToHost, e->stream));
@@ -259,6 +302,21 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   A(dalloc(&e->model.base, (size_t)P_COUNT * e->model.stride));
   A(dalloc(&e->model_alt.base, (size_t)P_COUNT * e->model_alt.stride));
   A(dalloc(&e->ftab, (size_t)2 * S)); A(dalloc(&e->matched, (size_t)S)); A(dalloc(&e->best, (size_t)S));
+  // second frame hand-over set + second stream for the pipelined mode (ssf_submit_frame)
+  e->slot[0].lmap = e->lmap; e->slot[0].frame = e->frame; e->slot[0].ftab = e->ftab;
+  e->slot[0].matched = e->matched; e->slot[0].best = e->best;
+  e->slot[1].frame.stride = e->frame.stride;
+  A(dalloc(&e->slot[1].lmap, N)); A(dalloc(&e->slot[1].frame.base, (size_t)P_COUNT * e->frame.stride));
+  A(dalloc(&e->slot[1].ftab, (size_t)2 * S)); A(dalloc(&e->slot[1].matched, (size_t)S)); A(dalloc(&e->slot[1].best, (size_t)S));
+  A(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; k++) {
+    A(cudaEventCreateWithFlags(&e->ev_seg[k], cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
+    A(cudaEventCreate(&e->ev_t0[k])); A(cudaEventCreate(&e->ev_t1[k]));
+    A(dalloc(&e->d_report2[k], (size_t)1));
+    A(cudaMallocHost(reinterpret_cast<void**>(&e->h_report2[k]), sizeof(FrameReport)));
+    A(cudaMallocHost(reinterpret_cast<void**>(&e->h_prior2[k]), 12 * sizeof(float)));
+  }
   A(dalloc(&e->states, (size_t)e->cap));
   A(dalloc(&e->scan_tmp, (size_t)8 + 4 * ((size_t)(e->cap + 1023) / 1024)));
   A(dalloc(&e->icp, (size_t)1)); A(dalloc(&e->icp_partials, (size_t)e->icp_grid * 32));
@@ -294,6 +352,23 @@ int ssf_destroy(SsfHandle h) {
   cudaDeviceSynchronize();
   for (int k = 0; k < 2; k++)
     if (e->graph_ready[k]) cudaGraphExecDestroy(e->graph_exec[k]);
+  if (e->slot[0].lmap) select_slot(e, 0);
+  for (int k = 0; k < 2; k++) {
+    for (int b = 0; b < 2; b++)
+      if (e->seg_ready[k][b]) cudaGraphExecDestroy(e->seg_graph[k][b]);
+    if (e->track_ready[k]) cudaGraphExecDestroy(e->track_graph[k]);
+    if (e->ev_seg[k]) cudaEventDestroy(e->ev_seg[k]);
+    if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
+    if (e->ev_t0[k]) cudaEventDestroy(e->ev_t0[k]);
+    if (e->ev_t1[k]) cudaEventDestroy(e->ev_t1[k]);
+    if (e->d_report2[k]) cudaFree(e->d_report2[k]);
+    if (e->h_report2[k]) cudaFreeHost(e->h_report2[k]);
+    if (e->h_prior2[k]) cudaFreeHost(e->h_prior2[k]);
+  }
+  void* slot1[] = {e->slot[1].lmap, e->slot[1].frame.base, e->slot[1].ftab, e->slot[1].matched, e->slot[1].best};
+  for (void* b : slot1)
+    if (b) cudaFree(b);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
   for (int g = 0; g < SSF_MAX_PEERS; g++)
     if (e->xpeer_open[g]) cudaIpcCloseMemHandle(e->xpeer_open[g]);
   void* bufs[] = {e->rgba, e->disp, e->labels, e->bound, e->inliers, e->lmap, e->in_rgb, e->in_depth, e->depth_f, e->in_depth16, e->sp, e->sums,
@@ -318,8 +393,12 @@ int ssf_set_stream(SsfHandle h, void* cuda_stream) {
   H_CHECK(h);
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
-  for (int k = 0; k < 2; k++)
+  for (int k = 0; k < 2; k++) {
     if (e->graph_ready[k]) { cudaGraphExecDestroy(e->graph_exec[k]); e->graph_ready[k] = false; }
+    for (int b = 0; b < 2; b++)
+      if (e->seg_ready[k][b]) { cudaGraphExecDestroy(e->seg_graph[k][b]); e->seg_ready[k][b] = false; }
+    if (e->track_ready[k]) { cudaGraphExecDestroy(e->track_graph[k]); e->track_ready[k] = false; }
+  }
   return SSF_OK;
 }
 
@@ -332,6 +411,8 @@ int ssf_is_initialized(SsfHandle h) { return (h && static_cast<EngineImpl*>(h)->
 
 static int run_frame(EngineImpl* e, const float* prior, uint32_t flags) {
   const int gi = (flags & SSF_FLAG_BILATERAL) ? 1 : 0;
+  if (e->in_flight) { e->err = "synchronous frame while pipelined frames are in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
+  if (e->cur_slot != 0) select_slot(e, 0);
   if (prior) {
     memcpy(e->h_prior, prior, 12 * sizeof(float));
     SSF_CUDA(e, cudaMemcpyAsync(e->pose, e->h_prior, 12 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
@@ -435,6 +516,99 @@ int ssf_get_filtered_depth(SsfHandle h, float* depth) {
   return SSF_OK;
 }
 
+// ---- pipelined mode ---------------------------------------------------------------------
+// Segmentation + extraction of a frame depend only on its images, registration + fusion on the
+// model: frame k+1's first stage runs on `stream` while frame k's second stage runs on
+// `stream2`, each a CUDA graph, chained by events; the two stages hand over through one of two
+// FrameOut sets.  Results are identical to the synchronous path (same kernels, same order per
+// stage); throughput is bounded by the longer stage instead of their sum.
+static int capture_graph(EngineImpl* e, cudaGraphExec_t* exec, uint64_t* launches, int what, bool bilateral, int slot) {
+  cudaGraph_t g;
+  const uint64_t before = e->launches;
+  SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  if (what == 0) {
+    enqueue_seg(e, bilateral);
+    launch_pdl(e, seg_end_kernel, dim3(1), dim3(1), 0, e->counters);
+    e->launches++;
+  } else {
+    enqueue_track(e, e->d_report2[slot], 1);
+  }
+  SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
+  *launches = e->launches - before;
+  e->launches = before;
+  SSF_CUDA(e, cudaGraphInstantiate(exec, g, 0));
+  cudaGraphDestroy(g);
+  return SSF_OK;
+}
+
+int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth, size_t depth_stride,
+                     const float* pose_prior_Rt12, uint32_t flags) {
+  H_CHECK(h);
+  if (!rgb || !depth) return SSF_ERR_INVALID_ARG;
+  if (rgb_stride == 0) rgb_stride = (size_t)e->W * 3;
+  if (depth_stride == 0) depth_stride = (size_t)e->W * 4;
+  if (rgb_stride < (size_t)e->W * 3 || depth_stride < (size_t)e->W * 4) return SSF_ERR_INVALID_ARG;
+  if (e->in_flight >= 2) { e->err = "two frames already in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
+  const int s = e->pipe_next;
+  const int gi = (flags & SSF_FLAG_BILATERAL) ? 1 : 0;
+  select_slot(e, s);
+  if (!e->seg_ready[s][gi]) {
+    int rc = capture_graph(e, &e->seg_graph[s][gi], &e->seg_launches[s][gi], 0, gi != 0, s);
+    if (rc) return rc;
+    e->seg_ready[s][gi] = true;
+  }
+  if (!e->track_ready[s]) {
+    int rc = capture_graph(e, &e->track_graph[s], &e->track_launches[s], 1, false, s);
+    if (rc) return rc;
+    e->track_ready[s] = true;
+  }
+  if (e->in_flight == 0) e->pipe_oldest = s;
+  // stage 1 on `stream`: wait until the tracking stage that last read this slot is done
+  SSF_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_done[s], 0));
+  SSF_CUDA(e, cudaEventRecord(e->ev_t0[s], e->stream));
+  SSF_CUDA(e, cudaMemcpy2DAsync(e->in_rgb, (size_t)e->W * 3, rgb, rgb_stride, (size_t)e->W * 3, e->H, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaMemcpy2DAsync(e->in_depth, (size_t)e->W * 4, depth, depth_stride, (size_t)e->W * 4, e->H, cudaMemcpyDefault, e->stream));
+  SSF_CUDA(e, cudaGraphLaunch(e->seg_graph[s][gi], e->stream));
+  SSF_CUDA(e, cudaEventRecord(e->ev_seg[s], e->stream));
+  // stage 2 on `stream2`
+  SSF_CUDA(e, cudaStreamWaitEvent(e->stream2, e->ev_seg[s], 0));
+  if (pose_prior_Rt12) {
+    memcpy(e->h_prior2[s], pose_prior_Rt12, 12 * sizeof(float));
+    SSF_CUDA(e, cudaMemcpyAsync(e->pose, e->h_prior2[s], 12 * sizeof(float), cudaMemcpyHostToDevice, e->stream2));
+  }
+  SSF_CUDA(e, cudaGraphLaunch(e->track_graph[s], e->stream2));
+  SSF_CUDA(e, cudaEventRecord(e->ev_t1[s], e->stream2));
+  SSF_CUDA(e, cudaMemcpyAsync(e->h_report2[s], e->d_report2[s], sizeof(FrameReport), cudaMemcpyDeviceToHost, e->stream2));
+  SSF_CUDA(e, cudaEventRecord(e->ev_done[s], e->stream2));
+  e->launches += e->seg_launches[s][gi] + e->track_launches[s];
+  e->in_flight++;
+  e->pipe_next = 1 - s;
+  return SSF_OK;
+}
+
+int ssf_wait_frame(SsfHandle h, SsfFrameStats* out, float R[9], float t[3]) {
+  H_CHECK(h);
+  if (e->in_flight <= 0) { e->err = "no frame in flight"; return SSF_ERR_STATE; }
+  const int s = e->pipe_oldest;
+  SSF_CUDA(e, cudaEventSynchronize(e->ev_done[s]));
+  SSF_CUDA(e, cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e->ev_t0[s], e->ev_t1[s]);
+  *e->h_report = *e->h_report2[s];
+  fill_stats(e, ms);
+  if (out) *out = e->stats;
+  if (R) memcpy(R, e->h_report->pose.R, 36);
+  if (t) memcpy(t, e->h_report->pose.t, 12);
+  e->in_flight--;
+  e->pipe_oldest = 1 - s;
+  if (e->in_flight == 0) {
+    // back to a quiescent state: every getter / stage entry point works on `stream` again
+    SSF_CUDA(e, cudaStreamSynchronize(e->stream2));
+    select_slot(e, s);
+  }
+  return SSF_OK;
+}
+
 int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out) {
   H_CHECK(h);
   if (!out) return SSF_ERR_INVALID_ARG;
@@ -471,6 +645,7 @@ int ssf_get_stamp(SsfHandle h, int* stamp) {
 int ssf_set_stamp(SsfHandle h, int stamp) {
   H_CHECK(h);
   SSF_CUDA(e, cudaMemcpyAsync(&e->counters->stamp, &stamp, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  SSF_CUDA(e, cudaMemcpyAsync(&e->counters->seg_stamp, &stamp, sizeof(int), cudaMemcpyHostToDevice, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   return SSF_OK;
 }

@@ -76,15 +76,30 @@ struct Counters {
   int nb_supersurfels, nb_visible, nb_removed, nb_matched, nb_inserted;
   int stamp;
   int cloud_count;
-  int pad;
+  int pad;         // scratch of the partition kernels (pre-compaction length)
+  int seg_stamp;   // stamp of the frame being segmented / extracted (runs ahead of `stamp` when pipelined)
+  int pad2;
 };
 
 struct DevicePose { float R[9]; float t[3]; };
+
+// What segmentation + extraction of a frame hand to registration + fusion.  Two sets, so that
+// the segmentation of frame k+1 can overlap the tracking of frame k (ssf_submit_frame).
+struct FrameOut {
+  int2* lmap;
+  SurfelSet frame;
+  float4* ftab;
+  unsigned char* matched;
+  unsigned long long* best;
+};
 
 struct Engine {
   SsfConfig cfg;
   int device;
   cudaStream_t own_stream, stream;
+  cudaStream_t stream2;      // registration + fusion stage of the pipelined mode
+  FrameOut slot[2];          // slot[0] is what the synchronous entry points use
+  int cur_slot;
   cudaEvent_t ev0, ev1, evf0, evf1;
   std::string err;
   uint64_t launches;

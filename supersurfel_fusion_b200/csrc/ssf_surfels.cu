@@ -137,7 +137,7 @@ __global__ void extract_finalize_kernel(SurfelSet frame, float4* ftab, unsigned 
     V3 vals;
     eigenframe(shape, orient, vals);
     d0 = vals.x; d1 = vals.y;
-    s0 = s1 = counters->stamp;
+    s0 = s1 = counters->seg_stamp;   // == stamp, except in the pipelined mode where segmentation runs a frame ahead
     if (vals.x / vals.y > 50.0f) conf = -1.0f;
   } else {
     conf = -1.0f;

@@ -64,7 +64,7 @@ SSF_FLAG_BILATERAL = 1   # include/ssf.h
 EXPORTS = [
     "ssf_config_default", "ssf_create", "ssf_destroy", "ssf_set_stream", "ssf_last_error", "ssf_is_initialized",
     "ssf_process_frame", "ssf_process_frame_depth16", "ssf_process_frame_device", "ssf_bilateral_filter",
-    "ssf_get_filtered_depth", "ssf_get_gray", "ssf_get_frame_stats", "ssf_get_pose", "ssf_set_pose",
+    "ssf_get_filtered_depth", "ssf_get_gray", "ssf_get_frame_stats", "ssf_submit_frame", "ssf_wait_frame", "ssf_get_pose", "ssf_set_pose",
     "ssf_get_stamp", "ssf_set_stamp", "ssf_get_counts", "ssf_get_nb_superpixels", "ssf_copy_model",
     "ssf_copy_frame", "ssf_get_segmentation", "ssf_render_preview", "ssf_get_slanted_depth", "ssf_export_model",
     "ssf_extract_local_point_cloud", "ssf_invalidate_frame_supersurfels", "ssf_transform_model", "ssf_set_model",
@@ -99,6 +99,8 @@ def load_library():
                                              C.c_void_p]
         lib.ssf_get_filtered_depth.argtypes = [C.c_void_p, C.c_void_p]
         lib.ssf_get_gray.argtypes = [C.c_void_p, C.c_void_p]
+        lib.ssf_submit_frame.argtypes = lib.ssf_process_frame.argtypes
+        lib.ssf_wait_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ssf_process_frame_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         lib.ssf_tps_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         lib.ssf_icp_system.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -293,6 +295,24 @@ class SupersurfelFusion:
         out = np.empty((self.height, self.width), np.uint8)
         self._check(self._lib.ssf_get_gray(self._h, _ptr(out)), "ssf_get_gray")
         return out
+
+    def submitFrame(self, rgb, depth, pose_prior=None, flags=0):
+        """Pipelined processFrame: enqueue and return (numpy arrays, pinned host or device torch tensors;
+        the buffers must stay alive until waitFrame() returned this frame).  Up to two frames in flight."""
+        prior = None
+        if pose_prior is not None:
+            R, t = pose_prior
+            prior = np.concatenate([np.asarray(R, np.float32).reshape(9), np.asarray(t, np.float32).reshape(3)])
+        rc = self._lib.ssf_submit_frame(self._h, _ptr(rgb), self.width * 3, _ptr(depth), self.width * 4, _ptr(prior), flags)
+        self._check(rc, "ssf_submit_frame")
+
+    def waitFrame(self):
+        """Blocks until the oldest submitted frame is done; returns (stats, R, t)."""
+        st = SsfFrameStats()
+        R = np.zeros(9, np.float32)
+        t = np.zeros(3, np.float32)
+        self._check(self._lib.ssf_wait_frame(self._h, C.byref(st), _ptr(R), _ptr(t)), "ssf_wait_frame")
+        return {k: getattr(st, k) for k, _ in SsfFrameStats._fields_}, R.reshape(3, 3), t
 
     def processFrameDevice(self, rgb_dev, depth_dev, pose_prior=None, flags=0):
         prior = None

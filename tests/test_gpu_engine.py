@@ -141,3 +141,43 @@ def test_export_model_format(orc, tmp_path):
     assert len(pos) == int((m.confidences >= 400.0).sum()) or len(pos) <= m.n
     assert geng.computeSuperpixelSegIm().shape == (240, 320, 3)
     assert np.array_equal(geng.computeSlantedPlaneIm(), geng.getSegmentation()["slanted"], equal_nan=True)
+
+
+def test_pipelined_frames_equal_synchronous_frames(orc):
+    """ssf_submit_frame / ssf_wait_frame (segmentation of frame k+1 overlapping the tracking of frame k on a
+    second stream) must give bit-identical stats, poses and models to ssf_process_frame."""
+    from supersurfel_fusion_b200 import CamParam, SupersurfelFusion
+    seq = SyntheticSequence(width=320, height=240, seed=31)
+    cam = CamParam(*seq.cam_param())
+    params = dict(TUM_PARAMS, nb_supersurfels_max=20000)
+    frames = [seq.frame(k) for k in range(12)]
+    sync = SupersurfelFusion().initialize(cam, **params)
+    want = []
+    for rgb, depth in frames:
+        st = sync.processFrame(rgb, depth)
+        want.append((st, sync.getPose()))
+    pipe = SupersurfelFusion().initialize(cam, **params)
+    got = []
+    pipe.submitFrame(*frames[0])
+    for k in range(1, len(frames)):
+        pipe.submitFrame(*frames[k])          # frame k enters while frame k-1 is still being tracked
+        got.append(pipe.waitFrame())
+    got.append(pipe.waitFrame())
+    for k, ((st_w, (R_w, t_w)), (st_g, R_g, t_g)) in enumerate(zip(want, got)):
+        for key in ("stamp", "nb_supersurfels", "nb_visible", "nb_removed", "nb_matched", "nb_inserted", "icp_valid", "icp_iters"):
+            assert st_g[key] == st_w[key], (k, key, st_g, st_w)
+        assert np.array_equal(R_g, R_w) and np.array_equal(t_g, t_w), k
+    n = sync.getCounts()[0]
+    ms, mp = sync.getModel(n), pipe.getModel(n)
+    assert np.array_equal(ms.positions, mp.positions) and np.array_equal(ms.confidences, mp.confidences)
+    assert np.array_equal(ms.stamps, mp.stamps)
+    assert np.array_equal(sync.getSegmentation()["labels"], pipe.getSegmentation()["labels"])
+    # a third frame in flight, and a synchronous call while frames are in flight, are refused
+    pipe.submitFrame(*frames[0]); pipe.submitFrame(*frames[1])
+    with pytest.raises(Exception):
+        pipe.submitFrame(*frames[2])
+    with pytest.raises(Exception):
+        pipe.processFrame(*frames[2])
+    pipe.waitFrame(); pipe.waitFrame()
+    pipe.processFrame(*frames[2])             # and it works again once the pipeline has drained
+    sync.close(); pipe.close()
