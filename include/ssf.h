@@ -145,9 +145,10 @@ int ssf_process_frame_device(SsfHandle h, const uint8_t* rgb_dev, const float* d
 int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out);
 /* Pipelined form of processFrame for streams of frames: ssf_submit_frame() enqueues a frame and
  * returns at once, ssf_wait_frame() blocks until the OLDEST submitted frame is done and returns
- * its stats and pose.  Up to two frames may be in flight: the segmentation + extraction of frame
- * k+1 (which depend only on its images) overlap the registration + fusion of frame k on a second
- * stream.  Same kernels, same order per stage: results are identical to ssf_process_frame; the
+ * its stats and pose.  Up to three frames may be in flight, one per stage: the colour-only
+ * segmentation iterations of frame k+2 (which need only its images), the rest of the segmentation
+ * + extraction of frame k+1, and the registration + fusion of frame k run concurrently on three
+ * streams.  Same kernels, same order per frame: results are identical to ssf_process_frame; the
  * input buffers must stay valid until the frame has been waited for (pinned host memory or
  * device memory for a truly asynchronous copy).  The synchronous entry points and the getters
  * require that no frame is in flight. */

@@ -56,18 +56,16 @@ __global__ void split_lmap_kernel(const int2* lmap, float* slanted, size_t n) {
 }
 
 struct EngineImpl : public SsfEngine {
-  // pipelined mode (ssf_submit_frame / ssf_wait_frame): per slot, a segmentation graph per ingest
-  // variant on `stream`, a tracking graph on `stream2`, their events, report and prior buffers
-  cudaGraphExec_t seg_graph[2][2];
-  bool seg_ready[2][2];
-  uint64_t seg_launches[2][2];
-  cudaGraphExec_t track_graph[2];
-  bool track_ready[2];
-  uint64_t track_launches[2];
-  cudaEvent_t ev_seg[2], ev_done[2], ev_t0[2], ev_t1[2];
-  FrameReport* d_report2[2];
-  FrameReport* h_report2[2];
-  float* h_prior2[2];
+  // pipelined mode (ssf_submit_frame / ssf_wait_frame): per slot three stage graphs -- A: ingest +
+  // colour-only segmentation iterations (one per ingest variant), B: RANSAC + colour/disparity
+  // iterations + smoothing + render + extraction, C: registration + fusion -- on three streams
+  cudaGraphExec_t graph_a[SSF_SLOTS][2], graph_b[SSF_SLOTS], graph_c[SSF_SLOTS];
+  bool ready_a[SSF_SLOTS][2], ready_b[SSF_SLOTS], ready_c[SSF_SLOTS];
+  uint64_t launches_a[SSF_SLOTS][2], launches_b[SSF_SLOTS], launches_c[SSF_SLOTS];
+  cudaEvent_t ev_a[SSF_SLOTS], ev_b[SSF_SLOTS], ev_done[SSF_SLOTS], ev_t0[SSF_SLOTS], ev_t1[SSF_SLOTS];
+  FrameReport* d_report2[SSF_SLOTS];
+  FrameReport* h_report2[SSF_SLOTS];
+  float* h_prior2[SSF_SLOTS];
   int pipe_next;     // slot of the next submitted frame
   int pipe_oldest;   // slot of the oldest frame in flight
   int in_flight;
@@ -94,29 +92,38 @@ static cudaError_t dalloc(T** p, size_t count) {
 static const int kBilateralKernel = -1;
 static const float kBilateralSigmaColor = 0.03f, kBilateralSigmaSpatial = 4.5f;
 
-// point the engine at one of the two frame hand-over sets
+// point the engine at one of the frame slots
 static void select_slot(EngineImpl* e, int s) {
+  const FrameSlot& f = e->slot[s];
   e->cur_slot = s;
-  e->lmap = e->slot[s].lmap;
-  e->frame = e->slot[s].frame;
-  e->ftab = e->slot[s].ftab;
-  e->matched = e->slot[s].matched;
-  e->best = e->slot[s].best;
+  e->rgba = f.rgba; e->disp = f.disp; e->labels = f.labels; e->bound = f.bound; e->inliers = f.inliers;
+  e->sp = f.sp; e->sums = f.sums;
+  e->lmap = f.lmap; e->frame = f.frame; e->ftab = f.ftab; e->matched = f.matched; e->best = f.best;
 }
 
-// stage 1: ingest + segmentation + extraction (reads the inputs, writes the selected FrameOut)
-static void enqueue_seg(EngineImpl* e, bool bilateral) {
+// stage A: ingest + the colour-only segmentation iterations (reads the inputs, writes the slot's images)
+static void enqueue_stage_a(EngineImpl* e, bool bilateral) {
   const float* depth = e->in_depth;
   if (bilateral) {
     launch_bilateral(e, e->in_depth, e->depth_f, kBilateralKernel, kBilateralSigmaColor, kBilateralSigmaSpatial);
     depth = e->depth_f;
   }
   launch_ingest(e, e->in_rgb, (size_t)e->W * 3, depth, (size_t)e->W * 4);
-  launch_tps(e);
+  launch_tps(e, 1);
+}
+
+// stage B: the rest of the segmentation + extraction (writes the slot's hand-over set)
+static void enqueue_stage_b(EngineImpl* e) {
+  launch_tps(e, 2);
   launch_extract(e);
 }
 
-// stage 2: registration + fusion (reads the selected FrameOut, owns pose / model / counters)
+static void enqueue_seg(EngineImpl* e, bool bilateral) {
+  enqueue_stage_a(e, bilateral);
+  enqueue_stage_b(e);
+}
+
+// stage C: registration + fusion (reads the slot's hand-over set, owns pose / model / counters)
 static void enqueue_track(EngineImpl* e, FrameReport* report, int advance) {
   launch_icp_begin_from_pose(e);
   launch_icp_loop(e);
@@ -302,15 +309,26 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   A(dalloc(&e->model.base, (size_t)P_COUNT * e->model.stride));
   A(dalloc(&e->model_alt.base, (size_t)P_COUNT * e->model_alt.stride));
   A(dalloc(&e->ftab, (size_t)2 * S)); A(dalloc(&e->matched, (size_t)S)); A(dalloc(&e->best, (size_t)S));
-  // second frame hand-over set + second stream for the pipelined mode (ssf_submit_frame)
-  e->slot[0].lmap = e->lmap; e->slot[0].frame = e->frame; e->slot[0].ftab = e->ftab;
-  e->slot[0].matched = e->matched; e->slot[0].best = e->best;
-  e->slot[1].frame.stride = e->frame.stride;
-  A(dalloc(&e->slot[1].lmap, N)); A(dalloc(&e->slot[1].frame.base, (size_t)P_COUNT * e->frame.stride));
-  A(dalloc(&e->slot[1].ftab, (size_t)2 * S)); A(dalloc(&e->slot[1].matched, (size_t)S)); A(dalloc(&e->slot[1].best, (size_t)S));
+  // slot 0 = the buffers above; two more frame slots, two more streams for the pipelined mode
+  {
+    FrameSlot& f = e->slot[0];
+    f.rgba = e->rgba; f.disp = e->disp; f.labels = e->labels; f.bound = e->bound; f.inliers = e->inliers;
+    f.sp = e->sp; f.sums = e->sums;
+    f.lmap = e->lmap; f.frame = e->frame; f.ftab = e->ftab; f.matched = e->matched; f.best = e->best;
+  }
+  for (int k = 1; k < SSF_SLOTS; k++) {
+    FrameSlot& f = e->slot[k];
+    A(dalloc(&f.rgba, N)); A(dalloc(&f.disp, N)); A(dalloc(&f.labels, N)); A(dalloc(&f.bound, N)); A(dalloc(&f.inliers, N));
+    A(dalloc(&f.sp, (size_t)S)); A(dalloc(&f.sums, (size_t)S));
+    f.frame.stride = e->frame.stride;
+    A(dalloc(&f.lmap, N)); A(dalloc(&f.frame.base, (size_t)P_COUNT * e->frame.stride));
+    A(dalloc(&f.ftab, (size_t)2 * S)); A(dalloc(&f.matched, (size_t)S)); A(dalloc(&f.best, (size_t)S));
+  }
   A(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
-  for (int k = 0; k < 2; k++) {
-    A(cudaEventCreateWithFlags(&e->ev_seg[k], cudaEventDisableTiming));
+  A(cudaStreamCreateWithFlags(&e->stream3, cudaStreamNonBlocking));
+  for (int k = 0; k < SSF_SLOTS; k++) {
+    A(cudaEventCreateWithFlags(&e->ev_a[k], cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&e->ev_b[k], cudaEventDisableTiming));
     A(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
     A(cudaEventCreate(&e->ev_t0[k])); A(cudaEventCreate(&e->ev_t1[k]));
     A(dalloc(&e->d_report2[k], (size_t)1));
@@ -353,11 +371,13 @@ int ssf_destroy(SsfHandle h) {
   for (int k = 0; k < 2; k++)
     if (e->graph_ready[k]) cudaGraphExecDestroy(e->graph_exec[k]);
   if (e->slot[0].lmap) select_slot(e, 0);
-  for (int k = 0; k < 2; k++) {
+  for (int k = 0; k < SSF_SLOTS; k++) {
     for (int b = 0; b < 2; b++)
-      if (e->seg_ready[k][b]) cudaGraphExecDestroy(e->seg_graph[k][b]);
-    if (e->track_ready[k]) cudaGraphExecDestroy(e->track_graph[k]);
-    if (e->ev_seg[k]) cudaEventDestroy(e->ev_seg[k]);
+      if (e->ready_a[k][b]) cudaGraphExecDestroy(e->graph_a[k][b]);
+    if (e->ready_b[k]) cudaGraphExecDestroy(e->graph_b[k]);
+    if (e->ready_c[k]) cudaGraphExecDestroy(e->graph_c[k]);
+    if (e->ev_a[k]) cudaEventDestroy(e->ev_a[k]);
+    if (e->ev_b[k]) cudaEventDestroy(e->ev_b[k]);
     if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
     if (e->ev_t0[k]) cudaEventDestroy(e->ev_t0[k]);
     if (e->ev_t1[k]) cudaEventDestroy(e->ev_t1[k]);
@@ -365,10 +385,14 @@ int ssf_destroy(SsfHandle h) {
     if (e->h_report2[k]) cudaFreeHost(e->h_report2[k]);
     if (e->h_prior2[k]) cudaFreeHost(e->h_prior2[k]);
   }
-  void* slot1[] = {e->slot[1].lmap, e->slot[1].frame.base, e->slot[1].ftab, e->slot[1].matched, e->slot[1].best};
-  for (void* b : slot1)
-    if (b) cudaFree(b);
+  for (int k = 1; k < SSF_SLOTS; k++) {
+    FrameSlot& f = e->slot[k];
+    void* own[] = {f.rgba, f.disp, f.labels, f.bound, f.inliers, f.sp, f.sums, f.lmap, f.frame.base, f.ftab, f.matched, f.best};
+    for (void* b : own)
+      if (b) cudaFree(b);
+  }
   if (e->stream2) cudaStreamDestroy(e->stream2);
+  if (e->stream3) cudaStreamDestroy(e->stream3);
   for (int g = 0; g < SSF_MAX_PEERS; g++)
     if (e->xpeer_open[g]) cudaIpcCloseMemHandle(e->xpeer_open[g]);
   void* bufs[] = {e->rgba, e->disp, e->labels, e->bound, e->inliers, e->lmap, e->in_rgb, e->in_depth, e->depth_f, e->in_depth16, e->sp, e->sums,
@@ -393,11 +417,13 @@ int ssf_set_stream(SsfHandle h, void* cuda_stream) {
   H_CHECK(h);
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
-  for (int k = 0; k < 2; k++) {
+  for (int k = 0; k < 2; k++)
     if (e->graph_ready[k]) { cudaGraphExecDestroy(e->graph_exec[k]); e->graph_ready[k] = false; }
+  for (int k = 0; k < SSF_SLOTS; k++) {
     for (int b = 0; b < 2; b++)
-      if (e->seg_ready[k][b]) { cudaGraphExecDestroy(e->seg_graph[k][b]); e->seg_ready[k][b] = false; }
-    if (e->track_ready[k]) { cudaGraphExecDestroy(e->track_graph[k]); e->track_ready[k] = false; }
+      if (e->ready_a[k][b]) { cudaGraphExecDestroy(e->graph_a[k][b]); e->ready_a[k][b] = false; }
+    if (e->ready_b[k]) { cudaGraphExecDestroy(e->graph_b[k]); e->ready_b[k] = false; }
+    if (e->ready_c[k]) { cudaGraphExecDestroy(e->graph_c[k]); e->ready_c[k] = false; }
   }
   return SSF_OK;
 }
@@ -517,17 +543,21 @@ int ssf_get_filtered_depth(SsfHandle h, float* depth) {
 }
 
 // ---- pipelined mode ---------------------------------------------------------------------
-// Segmentation + extraction of a frame depend only on its images, registration + fusion on the
-// model: frame k+1's first stage runs on `stream` while frame k's second stage runs on
-// `stream2`, each a CUDA graph, chained by events; the two stages hand over through one of two
-// FrameOut sets.  Results are identical to the synchronous path (same kernels, same order per
-// stage); throughput is bounded by the longer stage instead of their sum.
-static int capture_graph(EngineImpl* e, cudaGraphExec_t* exec, uint64_t* launches, int what, bool bilateral, int slot) {
+// A frame passes three stages: A (ingest + the colour-only segmentation iterations) needs only its
+// images, B (RANSAC, colour + disparity iterations, smoothing, render, extraction) needs A, and C
+// (registration + fusion) needs B and the model.  Each stage is a CUDA graph on its own stream,
+// stages of one frame are chained by events, a stage of consecutive frames is serialised by its
+// stream, and every frame owns one of three slots -- so three consecutive frames are in three
+// different stages at once.  Same kernels in the same order per frame: results are identical to the
+// synchronous path; throughput is bounded by the longest stage instead of the sum of the three.
+static int capture_stage(EngineImpl* e, cudaGraphExec_t* exec, uint64_t* launches, int stage, bool bilateral, int slot) {
   cudaGraph_t g;
   const uint64_t before = e->launches;
   SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-  if (what == 0) {
-    enqueue_seg(e, bilateral);
+  if (stage == 0) {
+    enqueue_stage_a(e, bilateral);
+  } else if (stage == 1) {
+    enqueue_stage_b(e);
     launch_pdl(e, seg_end_kernel, dim3(1), dim3(1), 0, e->counters);
     e->launches++;
   } else {
@@ -548,41 +578,48 @@ int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const f
   if (rgb_stride == 0) rgb_stride = (size_t)e->W * 3;
   if (depth_stride == 0) depth_stride = (size_t)e->W * 4;
   if (rgb_stride < (size_t)e->W * 3 || depth_stride < (size_t)e->W * 4) return SSF_ERR_INVALID_ARG;
-  if (e->in_flight >= 2) { e->err = "two frames already in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
+  if (e->in_flight >= SSF_SLOTS) { e->err = "three frames already in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
   const int s = e->pipe_next;
   const int gi = (flags & SSF_FLAG_BILATERAL) ? 1 : 0;
   select_slot(e, s);
-  if (!e->seg_ready[s][gi]) {
-    int rc = capture_graph(e, &e->seg_graph[s][gi], &e->seg_launches[s][gi], 0, gi != 0, s);
-    if (rc) return rc;
-    e->seg_ready[s][gi] = true;
+  int rc = SSF_OK;
+  if (!e->ready_a[s][gi]) {
+    if ((rc = capture_stage(e, &e->graph_a[s][gi], &e->launches_a[s][gi], 0, gi != 0, s))) return rc;
+    e->ready_a[s][gi] = true;
   }
-  if (!e->track_ready[s]) {
-    int rc = capture_graph(e, &e->track_graph[s], &e->track_launches[s], 1, false, s);
-    if (rc) return rc;
-    e->track_ready[s] = true;
+  if (!e->ready_b[s]) {
+    if ((rc = capture_stage(e, &e->graph_b[s], &e->launches_b[s], 1, false, s))) return rc;
+    e->ready_b[s] = true;
+  }
+  if (!e->ready_c[s]) {
+    if ((rc = capture_stage(e, &e->graph_c[s], &e->launches_c[s], 2, false, s))) return rc;
+    e->ready_c[s] = true;
   }
   if (e->in_flight == 0) e->pipe_oldest = s;
-  // stage 1 on `stream`: wait until the tracking stage that last read this slot is done
+  // stage A on `stream`: the slot is free once the frame that last used it has been tracked
   SSF_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_done[s], 0));
   SSF_CUDA(e, cudaEventRecord(e->ev_t0[s], e->stream));
   SSF_CUDA(e, cudaMemcpy2DAsync(e->in_rgb, (size_t)e->W * 3, rgb, rgb_stride, (size_t)e->W * 3, e->H, cudaMemcpyDefault, e->stream));
   SSF_CUDA(e, cudaMemcpy2DAsync(e->in_depth, (size_t)e->W * 4, depth, depth_stride, (size_t)e->W * 4, e->H, cudaMemcpyDefault, e->stream));
-  SSF_CUDA(e, cudaGraphLaunch(e->seg_graph[s][gi], e->stream));
-  SSF_CUDA(e, cudaEventRecord(e->ev_seg[s], e->stream));
-  // stage 2 on `stream2`
-  SSF_CUDA(e, cudaStreamWaitEvent(e->stream2, e->ev_seg[s], 0));
+  SSF_CUDA(e, cudaGraphLaunch(e->graph_a[s][gi], e->stream));
+  SSF_CUDA(e, cudaEventRecord(e->ev_a[s], e->stream));
+  // stage B on `stream3`
+  SSF_CUDA(e, cudaStreamWaitEvent(e->stream3, e->ev_a[s], 0));
+  SSF_CUDA(e, cudaGraphLaunch(e->graph_b[s], e->stream3));
+  SSF_CUDA(e, cudaEventRecord(e->ev_b[s], e->stream3));
+  // stage C on `stream2`
+  SSF_CUDA(e, cudaStreamWaitEvent(e->stream2, e->ev_b[s], 0));
   if (pose_prior_Rt12) {
     memcpy(e->h_prior2[s], pose_prior_Rt12, 12 * sizeof(float));
     SSF_CUDA(e, cudaMemcpyAsync(e->pose, e->h_prior2[s], 12 * sizeof(float), cudaMemcpyHostToDevice, e->stream2));
   }
-  SSF_CUDA(e, cudaGraphLaunch(e->track_graph[s], e->stream2));
+  SSF_CUDA(e, cudaGraphLaunch(e->graph_c[s], e->stream2));
   SSF_CUDA(e, cudaEventRecord(e->ev_t1[s], e->stream2));
   SSF_CUDA(e, cudaMemcpyAsync(e->h_report2[s], e->d_report2[s], sizeof(FrameReport), cudaMemcpyDeviceToHost, e->stream2));
   SSF_CUDA(e, cudaEventRecord(e->ev_done[s], e->stream2));
-  e->launches += e->seg_launches[s][gi] + e->track_launches[s];
+  e->launches += e->launches_a[s][gi] + e->launches_b[s] + e->launches_c[s];
   e->in_flight++;
-  e->pipe_next = 1 - s;
+  e->pipe_next = (s + 1) % SSF_SLOTS;
   return SSF_OK;
 }
 
@@ -600,9 +637,11 @@ int ssf_wait_frame(SsfHandle h, SsfFrameStats* out, float R[9], float t[3]) {
   if (R) memcpy(R, e->h_report->pose.R, 36);
   if (t) memcpy(t, e->h_report->pose.t, 12);
   e->in_flight--;
-  e->pipe_oldest = 1 - s;
+  e->pipe_oldest = (s + 1) % SSF_SLOTS;
   if (e->in_flight == 0) {
-    // back to a quiescent state: every getter / stage entry point works on `stream` again
+    // back to a quiescent state: every getter / stage entry point works on `stream` and on the
+    // slot of the frame just returned
+    SSF_CUDA(e, cudaStreamSynchronize(e->stream3));
     SSF_CUDA(e, cudaStreamSynchronize(e->stream2));
     select_slot(e, s);
   }

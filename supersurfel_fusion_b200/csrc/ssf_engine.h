@@ -83,9 +83,18 @@ struct Counters {
 
 struct DevicePose { float R[9]; float t[3]; };
 
-// What segmentation + extraction of a frame hand to registration + fusion.  Two sets, so that
-// the segmentation of frame k+1 can overlap the tracking of frame k (ssf_submit_frame).
-struct FrameOut {
+// Everything that belongs to ONE frame on its way through the stages: the segmentation images and
+// per-superpixel state, and what segmentation + extraction hand to registration + fusion.  Three
+// sets, so that three consecutive frames can be in three different stages (ssf_submit_frame).
+constexpr int SSF_SLOTS = 3;
+struct FrameSlot {
+  uchar4* rgba;
+  float* disp;
+  int* labels;
+  int* bound;
+  unsigned char* inliers;
+  Superpixel* sp;
+  SpSums* sums;
   int2* lmap;
   SurfelSet frame;
   float4* ftab;
@@ -97,8 +106,8 @@ struct Engine {
   SsfConfig cfg;
   int device;
   cudaStream_t own_stream, stream;
-  cudaStream_t stream2;      // registration + fusion stage of the pipelined mode
-  FrameOut slot[2];          // slot[0] is what the synchronous entry points use
+  cudaStream_t stream2, stream3;   // pipelined mode: registration + fusion stage, second segmentation stage
+  FrameSlot slot[SSF_SLOTS];       // slot[0] is what the synchronous entry points use
   int cur_slot;
   cudaEvent_t ev0, ev1, evf0, evf1;
   std::string err;
@@ -213,7 +222,7 @@ float icp_lab_gate_sq();
 float icp_dist_gate_sq();
 void launch_ingest(Engine* e, const uint8_t* rgb_dev, size_t rgb_stride, const float* depth_dev,
                    size_t depth_stride);
-void launch_tps(Engine* e);
+void launch_tps(Engine* e, int part = 0);
 void launch_extract(Engine* e);
 void launch_fuse(Engine* e);
 void launch_build_lmap(Engine* e, const float* slanted_dev);

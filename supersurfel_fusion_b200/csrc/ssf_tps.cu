@@ -921,10 +921,14 @@ static void launch_pass(Engine* e, const TpsArgs& a, int OX, int OY) {
   e->launches += 2;
 }
 
-void launch_tps(Engine* e) {
+// part 0 = the whole segmentation; 1 = the colour-only iterations (they need nothing but the seeded
+// images); 2 = everything after them (RANSAC, colour + disparity iterations, smoothing, render).  The
+// pipelined mode runs parts 1 and 2 of consecutive frames on different streams.
+void launch_tps(Engine* e, int part) {
   TpsArgs a = tps_args(e);
   const int nbIters = e->cfg.seg_iter;
   if (e->tps_persistent) {
+    if (part == 1) return;             // the one-kernel form is not split: it runs as part 2
     TpsRun r;
     r.nb_iters = nbIters; r.use_ransac = e->cfg.seg_use_ransac; r.nb_samples = e->cfg.nb_samples;
     r.filter_iters = e->cfg.filter_iter;
@@ -945,12 +949,15 @@ void launch_tps(Engine* e) {
     e->launches++;
     return;
   }
-  for (int k = 0; k < nbIters / 2; k++) {
-    launch_pass<false>(e, a, 0, 0);
-    launch_pass<false>(e, a, 1, 1);
-    launch_pass<false>(e, a, 0, 1);
-    launch_pass<false>(e, a, 1, 0);
+  if (part != 2) {
+    for (int k = 0; k < nbIters / 2; k++) {
+      launch_pass<false>(e, a, 0, 0);
+      launch_pass<false>(e, a, 1, 1);
+      launch_pass<false>(e, a, 0, 1);
+      launch_pass<false>(e, a, 1, 0);
+    }
   }
+  if (part == 1) return;
   dim3 blk(32, 8), grd(cdiv(e->W, 32), cdiv(e->H, 8));
   if (e->cfg.seg_use_ransac) {
     int* votes = reinterpret_cast<int*>(e->samples + (size_t)e->S * e->cfg.nb_samples);

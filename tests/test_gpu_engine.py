@@ -144,8 +144,8 @@ def test_export_model_format(orc, tmp_path):
 
 
 def test_pipelined_frames_equal_synchronous_frames(orc):
-    """ssf_submit_frame / ssf_wait_frame (segmentation of frame k+1 overlapping the tracking of frame k on a
-    second stream) must give bit-identical stats, poses and models to ssf_process_frame."""
+    """ssf_submit_frame / ssf_wait_frame (three frames in flight, one per stage, on three streams) must give
+    bit-identical stats, poses and models to ssf_process_frame."""
     from supersurfel_fusion_b200 import CamParam, SupersurfelFusion
     seq = SyntheticSequence(width=320, height=240, seed=31)
     cam = CamParam(*seq.cam_param())
@@ -159,9 +159,11 @@ def test_pipelined_frames_equal_synchronous_frames(orc):
     pipe = SupersurfelFusion().initialize(cam, **params)
     got = []
     pipe.submitFrame(*frames[0])
-    for k in range(1, len(frames)):
-        pipe.submitFrame(*frames[k])          # frame k enters while frame k-1 is still being tracked
+    pipe.submitFrame(*frames[1])
+    for k in range(2, len(frames)):
+        pipe.submitFrame(*frames[k])          # frame k enters while frames k-1 and k-2 are still in later stages
         got.append(pipe.waitFrame())
+    got.append(pipe.waitFrame())
     got.append(pipe.waitFrame())
     for k, ((st_w, (R_w, t_w)), (st_g, R_g, t_g)) in enumerate(zip(want, got)):
         for key in ("stamp", "nb_supersurfels", "nb_visible", "nb_removed", "nb_matched", "nb_inserted", "icp_valid", "icp_iters"):
@@ -172,12 +174,12 @@ def test_pipelined_frames_equal_synchronous_frames(orc):
     assert np.array_equal(ms.positions, mp.positions) and np.array_equal(ms.confidences, mp.confidences)
     assert np.array_equal(ms.stamps, mp.stamps)
     assert np.array_equal(sync.getSegmentation()["labels"], pipe.getSegmentation()["labels"])
-    # a third frame in flight, and a synchronous call while frames are in flight, are refused
-    pipe.submitFrame(*frames[0]); pipe.submitFrame(*frames[1])
+    # a fourth frame in flight, and a synchronous call while frames are in flight, are refused
+    pipe.submitFrame(*frames[0]); pipe.submitFrame(*frames[1]); pipe.submitFrame(*frames[2])
     with pytest.raises(Exception):
-        pipe.submitFrame(*frames[2])
+        pipe.submitFrame(*frames[3])
     with pytest.raises(Exception):
         pipe.processFrame(*frames[2])
-    pipe.waitFrame(); pipe.waitFrame()
+    pipe.waitFrame(); pipe.waitFrame(); pipe.waitFrame()
     pipe.processFrame(*frames[2])             # and it works again once the pipeline has drained
     sync.close(); pipe.close()

@@ -19,9 +19,11 @@ def run(bufs, pipelined, steps=300):
     t0 = time.perf_counter()
     if pipelined:
         eng.submitFrame(*bufs[bench.frame_index(10)])
-        for s in range(11, 10 + steps):
+        eng.submitFrame(*bufs[bench.frame_index(11)])
+        for s in range(12, 10 + steps):
             eng.submitFrame(*bufs[bench.frame_index(s)])
             eng.waitFrame()
+        eng.waitFrame()
         eng.waitFrame()
     else:
         for s in range(10, 10 + steps):
