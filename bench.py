@@ -13,7 +13,7 @@ Rank 0 prints ONE JSON line:
   value     frames/s with the frames already resident in HBM
   e2e       frames/s through the C-ABI with pinned HOST buffers: the H2D copy of the frame and
             the D2H read of the pose/stats are inside the timed region
-            (both through ssf_submit_frame / ssf_wait_frame, three frames in flight; the numbers
+            (both through ssf_submit_frame / ssf_wait_frame, one frame in flight per pipeline stage; the numbers
             of the synchronous ssf_process_frame, the reference's call shape, are reported
             under "synchronous"; --no-pipeline times only those)
   roofline  the ICP system kernel (the metric kernel) at HBM-bound sizing: 16 Mi source
@@ -43,7 +43,6 @@ PARAMS = dict(cell_size=16, lambda_pos=10.0, lambda_bound=1000.0, lambda_size=10
               filter_beta=1.0, filter_threshold=0.05, range_min=0.2, range_max=5.0, delta_t=20, conf_thresh=2560.0,
               nb_supersurfels_max=100000, icp_iter=10, icp_cov_thresh=0.05)   # launch/supersurfel_fusion_rgbd_benchmark.launch
 N_UNIQUE_FRAMES = 24
-PIPELINE_DEPTH = 3          # frames in flight through ssf_submit_frame / ssf_wait_frame (one per stage)
 ICP_BYTES_PER_SRC = 72
 ICP_ROOFLINE_N = 16 * 1024 * 1024
 
@@ -313,8 +312,8 @@ def run_ours(args, rank, world, local_rank):
     def timed(bufs, device_resident, pipelined, steps, warmup):
         """K frames through the engine after W warm-up frames; CUDA events on the engine's stream around the
         timed region (the pipeline is drained inside it), max over ranks.  pipelined: ssf_submit_frame /
-        ssf_wait_frame, the segmentation of frame k+1 overlapping the tracking of frame k (two frames in
-        flight, results identical to the synchronous call, tests/test_gpu_engine.py)."""
+        ssf_wait_frame, one frame in flight per pipeline stage (results identical to the synchronous
+        call, tests/test_gpu_engine.py)."""
         eng = SupersurfelFusion(dev).initialize(CamParam(*cam), **PARAMS)
 
         def sync_step(s):
@@ -331,13 +330,12 @@ def run_ours(args, rank, world, local_rank):
         eng.timerStart()                      # CUDA event on the engine's stream
         w0 = time.perf_counter()
         if pipelined:
-            depth = min(PIPELINE_DEPTH, steps)
-            for s in range(warmup, warmup + depth - 1):
+            depth = min(eng.pipelineDepth(), steps)
+            for s in range(warmup, warmup + steps):
+                if s - warmup >= depth:
+                    eng.waitFrame()               # `depth` frames in flight, one per stage
                 eng.submitFrame(*bufs[frame_index(s)])
-            for s in range(warmup + depth - 1, warmup + steps):
-                eng.submitFrame(*bufs[frame_index(s)])
-                eng.waitFrame()
-            for _ in range(depth - 1):
+            for _ in range(depth):
                 eng.waitFrame()
         else:
             for s in range(warmup, warmup + steps):
@@ -347,6 +345,7 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         launches = eng.launchCount() - l0
         stats = eng.getFrameStats()
+        stats["pipeline_depth"] = eng.pipelineDepth()
         eng.close()
         return max_over_ranks(ms), max_over_ranks(wall), launches, stats
 
@@ -388,6 +387,7 @@ def run_ours(args, rank, world, local_rank):
     pipelined = not args.no_pipeline
     ms, wall_ms, launches, stats = timed(dev_bufs, True, pipelined, args.steps, args.warmup)
     ms_e, wall_e, _, _ = timed(host_bufs, False, pipelined, args.steps, args.warmup)
+    pipe_depth = stats.pop("pipeline_depth")
     sync_ms = sync_ms_e = None
     if pipelined and not args.skip_extras:
         sync_ms = timed(dev_bufs, True, False, args.steps, args.warmup)[0]
@@ -428,9 +428,9 @@ def run_ours(args, rank, world, local_rank):
                    "params": "launch/supersurfel_fusion_rgbd_benchmark.launch", "frames_per_gpu": args.steps,
                    "l2_policy": "per-frame working set (~9 MB images + model) is L2 resident by nature of the workload; "
                                 "the roofline kernel streams 604 MB per launch (> 126 MB L2), no flush needed",
-                   "pipeline": ("ssf_submit_frame / ssf_wait_frame: three frames in flight, one per stage (colour-only segmentation "
-                                "iterations | rest of segmentation + extraction | registration + fusion) on three streams; identical results to the "
-                                "synchronous ssf_process_frame, whose numbers are under 'synchronous'") if pipelined
+                   "pipeline": ("ssf_submit_frame / ssf_wait_frame: the frame's kernel chain cut into %d stages of equal cost on "
+                                "separate streams, one frame in flight per stage; identical results to the synchronous "
+                                "ssf_process_frame, whose numbers are under 'synchronous'" % pipe_depth) if pipelined
                                else "synchronous ssf_process_frame, one frame at a time",
                    "timing": "CUDA events on the engine stream around all K frames (pipeline drained inside), max over ranks"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": SIZE[0] * SIZE[1] * 7, "d2h_bytes_per_step": 104,

@@ -145,16 +145,18 @@ int ssf_process_frame_device(SsfHandle h, const uint8_t* rgb_dev, const float* d
 int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out);
 /* Pipelined form of processFrame for streams of frames: ssf_submit_frame() enqueues a frame and
  * returns at once, ssf_wait_frame() blocks until the OLDEST submitted frame is done and returns
- * its stats and pose.  Up to three frames may be in flight, one per stage: the colour-only
- * segmentation iterations of frame k+2 (which need only its images), the rest of the segmentation
- * + extraction of frame k+1, and the registration + fusion of frame k run concurrently on three
- * streams.  Same kernels, same order per frame: results are identical to ssf_process_frame; the
- * input buffers must stay valid until the frame has been waited for (pinned host memory or
- * device memory for a truly asynchronous copy).  The synchronous entry points and the getters
- * require that no frame is in flight. */
+ * its stats and pose.  The frame's kernel sequence (ingest -> segmentation iterations -> extraction
+ * -> registration + fusion; only the last part touches the model) is cut into
+ * ssf_get_pipeline_depth() stages of about equal cost (default 4, SSF_PIPELINE_STAGES=1..6), each
+ * on its own stream, and that many frames may be in flight, one per stage.  Same kernels in the
+ * same order per frame: results are identical to ssf_process_frame; latency per frame is
+ * unchanged, the frame rate is set by the longest stage.  The input buffers must stay valid until
+ * the frame has been waited for (pinned host memory or device memory for a truly asynchronous
+ * copy).  The synchronous entry points and the getters require that no frame is in flight. */
 int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth,
                      size_t depth_stride, const float* pose_prior_Rt12, uint32_t flags);
 int ssf_wait_frame(SsfHandle h, SsfFrameStats* out, float R[9], float t[3]);
+int ssf_get_pipeline_depth(SsfHandle h, int* stages);
 
 /* ---- ingest (supersurfel_fusion.cu:171-181) -------------------------------- */
 /* cv::cuda::bilateralFilter(depth, depth, kernel_size, sigma_color, sigma_spatial)

@@ -56,13 +56,14 @@ __global__ void split_lmap_kernel(const int2* lmap, float* slanted, size_t n) {
 }
 
 struct EngineImpl : public SsfEngine {
-  // pipelined mode (ssf_submit_frame / ssf_wait_frame): per slot three stage graphs -- A: ingest +
-  // colour-only segmentation iterations (one per ingest variant), B: RANSAC + colour/disparity
-  // iterations + smoothing + render + extraction, C: registration + fusion -- on three streams
-  cudaGraphExec_t graph_a[SSF_SLOTS][2], graph_b[SSF_SLOTS], graph_c[SSF_SLOTS];
-  bool ready_a[SSF_SLOTS][2], ready_b[SSF_SLOTS], ready_c[SSF_SLOTS];
-  uint64_t launches_a[SSF_SLOTS][2], launches_b[SSF_SLOTS], launches_c[SSF_SLOTS];
-  cudaEvent_t ev_a[SSF_SLOTS], ev_b[SSF_SLOTS], ev_done[SSF_SLOTS], ev_t0[SSF_SLOTS], ev_t1[SSF_SLOTS];
+  // pipelined mode (ssf_submit_frame / ssf_wait_frame): the frame's launch sequence is cut into
+  // nb_stages contiguous stages (stage_first[p] .. stage_first[p+1]); per slot and stage one CUDA
+  // graph (two for the stage that holds the ingest: with / without the bilateral filter)
+  int stage_first[SSF_SLOTS + 1];
+  cudaGraphExec_t stage_graph[SSF_SLOTS][SSF_SLOTS][2];
+  bool stage_ready[SSF_SLOTS][SSF_SLOTS][2];
+  uint64_t stage_launches[SSF_SLOTS][SSF_SLOTS][2];
+  cudaEvent_t ev_stage[SSF_SLOTS][SSF_SLOTS], ev_done[SSF_SLOTS], ev_t0[SSF_SLOTS], ev_t1[SSF_SLOTS];
   FrameReport* d_report2[SSF_SLOTS];
   FrameReport* h_report2[SSF_SLOTS];
   float* h_prior2[SSF_SLOTS];
@@ -101,26 +102,71 @@ static void select_slot(EngineImpl* e, int s) {
   e->lmap = f.lmap; e->frame = f.frame; e->ftab = f.ftab; e->matched = f.matched; e->best = f.best;
 }
 
-// stage A: ingest + the colour-only segmentation iterations (reads the inputs, writes the slot's images)
-static void enqueue_stage_a(EngineImpl* e, bool bilateral) {
-  const float* depth = e->in_depth;
-  if (bilateral) {
-    launch_bilateral(e, e->in_depth, e->depth_f, kBilateralKernel, kBilateralSigmaColor, kBilateralSigmaSpatial);
-    depth = e->depth_f;
+// The frame as a sequence of steps: 0 = ingest, 1 .. T = the segmentation steps (tps_step_count),
+// T + 1 = extraction, T + 2 = registration + fusion.  enqueue_steps enqueues [g0, g1).
+static int frame_step_count(const EngineImpl* e) { return tps_step_count(e) + 3; }
+
+static void enqueue_track(EngineImpl* e, FrameReport* report, int advance);
+
+static void enqueue_steps(EngineImpl* e, int g0, int g1, bool bilateral, bool pipelined, FrameReport* report) {
+  const int T = tps_step_count(e);
+  if (g0 <= 0 && g1 > 0) {
+    const float* depth = e->in_depth;
+    if (bilateral) {
+      launch_bilateral(e, e->in_depth, e->depth_f, kBilateralKernel, kBilateralSigmaColor, kBilateralSigmaSpatial);
+      depth = e->depth_f;
+    }
+    launch_ingest(e, e->in_rgb, (size_t)e->W * 3, depth, (size_t)e->W * 4);
   }
-  launch_ingest(e, e->in_rgb, (size_t)e->W * 3, depth, (size_t)e->W * 4);
-  launch_tps(e, 1);
+  const int t0 = (g0 > 1 ? g0 : 1) - 1, t1 = (g1 < T + 1 ? g1 : T + 1) - 1;
+  if (t1 > t0) launch_tps(e, t0, t1);
+  if (g0 <= T + 1 && g1 > T + 1) {
+    launch_extract(e);
+    if (pipelined) {     // the next frame to be extracted carries the next stamp
+      launch_pdl(e, seg_end_kernel, dim3(1), dim3(1), 0, e->counters);
+      e->launches++;
+    }
+  }
+  if (g0 <= T + 2 && g1 > T + 2) enqueue_track(e, report, pipelined ? 1 : 3);
 }
 
-// stage B: the rest of the segmentation + extraction (writes the slot's hand-over set)
-static void enqueue_stage_b(EngineImpl* e) {
-  launch_tps(e, 2);
-  launch_extract(e);
+// Cut the steps into `stages` contiguous groups minimising the heaviest group (weights ~ kernel
+// launches of a step, the quantity that sets a stage's duration at VGA).
+static void plan_stages(EngineImpl* e, int stages) {
+  const int G = frame_step_count(e), T = tps_step_count(e), half = e->cfg.seg_iter / 2;
+  int w[64];
+  for (int g = 0; g < G; g++) {
+    if (g == 0) w[g] = 3;
+    else if (g <= T) {
+      const int t = g - 1;
+      w[g] = e->tps_persistent ? 60 : (t < half ? 8 : (t == half ? 6 : (t <= e->cfg.seg_iter ? 10 : 3)));
+    } else if (g == T + 1) w[g] = 3;
+    else w[g] = 12 + e->cfg.icp_iter;
+  }
+  if (stages > G) stages = G;
+  // dynamic programme: best[p][g] = minimal heaviest group when the first g steps form p groups
+  static const int INF = 1 << 28;
+  int best[SSF_SLOTS + 1][65], cut[SSF_SLOTS + 1][65];
+  for (int p = 0; p <= stages; p++)
+    for (int g = 0; g <= G; g++) best[p][g] = INF;
+  best[0][0] = 0;
+  for (int p = 1; p <= stages; p++)
+    for (int g = p; g <= G; g++) {
+      int sum = 0;
+      for (int k = g - 1; k >= p - 1; k--) {
+        sum += w[k];
+        const int cand = best[p - 1][k] > sum ? best[p - 1][k] : sum;
+        if (cand < best[p][g]) { best[p][g] = cand; cut[p][g] = k; }
+      }
+    }
+  e->nb_stages = stages;
+  int g = G;
+  for (int p = stages; p >= 1; p--) { e->stage_first[p] = g; g = cut[p][g]; }
+  e->stage_first[0] = 0;
 }
 
 static void enqueue_seg(EngineImpl* e, bool bilateral) {
-  enqueue_stage_a(e, bilateral);
-  enqueue_stage_b(e);
+  enqueue_steps(e, 0, tps_step_count(e) + 2, bilateral, false, nullptr);
 }
 
 // stage C: registration + fusion (reads the slot's hand-over set, owns pose / model / counters)
@@ -324,16 +370,21 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
     A(dalloc(&f.lmap, N)); A(dalloc(&f.frame.base, (size_t)P_COUNT * e->frame.stride));
     A(dalloc(&f.ftab, (size_t)2 * S)); A(dalloc(&f.matched, (size_t)S)); A(dalloc(&f.best, (size_t)S));
   }
-  A(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
-  A(cudaStreamCreateWithFlags(&e->stream3, cudaStreamNonBlocking));
+  for (int p = 1; p < SSF_SLOTS; p++) A(cudaStreamCreateWithFlags(&e->stage_stream[p], cudaStreamNonBlocking));
   for (int k = 0; k < SSF_SLOTS; k++) {
-    A(cudaEventCreateWithFlags(&e->ev_a[k], cudaEventDisableTiming));
-    A(cudaEventCreateWithFlags(&e->ev_b[k], cudaEventDisableTiming));
+    for (int p = 0; p < SSF_SLOTS; p++) A(cudaEventCreateWithFlags(&e->ev_stage[k][p], cudaEventDisableTiming));
     A(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
     A(cudaEventCreate(&e->ev_t0[k])); A(cudaEventCreate(&e->ev_t1[k]));
     A(dalloc(&e->d_report2[k], (size_t)1));
     A(cudaMallocHost(reinterpret_cast<void**>(&e->h_report2[k]), sizeof(FrameReport)));
     A(cudaMallocHost(reinterpret_cast<void**>(&e->h_prior2[k]), 12 * sizeof(float)));
+  }
+  {
+    int stages = 4;
+    if (const char* v = getenv("SSF_PIPELINE_STAGES")) stages = atoi(v);   // 1 .. 6 frames in flight
+    if (stages < 1) stages = 1;
+    if (stages > SSF_SLOTS) stages = SSF_SLOTS;
+    plan_stages(e, stages);
   }
   A(dalloc(&e->states, (size_t)e->cap));
   A(dalloc(&e->scan_tmp, (size_t)8 + 4 * ((size_t)(e->cap + 1023) / 1024)));
@@ -372,12 +423,11 @@ int ssf_destroy(SsfHandle h) {
     if (e->graph_ready[k]) cudaGraphExecDestroy(e->graph_exec[k]);
   if (e->slot[0].lmap) select_slot(e, 0);
   for (int k = 0; k < SSF_SLOTS; k++) {
-    for (int b = 0; b < 2; b++)
-      if (e->ready_a[k][b]) cudaGraphExecDestroy(e->graph_a[k][b]);
-    if (e->ready_b[k]) cudaGraphExecDestroy(e->graph_b[k]);
-    if (e->ready_c[k]) cudaGraphExecDestroy(e->graph_c[k]);
-    if (e->ev_a[k]) cudaEventDestroy(e->ev_a[k]);
-    if (e->ev_b[k]) cudaEventDestroy(e->ev_b[k]);
+    for (int p = 0; p < SSF_SLOTS; p++) {
+      for (int b = 0; b < 2; b++)
+        if (e->stage_ready[k][p][b]) cudaGraphExecDestroy(e->stage_graph[k][p][b]);
+      if (e->ev_stage[k][p]) cudaEventDestroy(e->ev_stage[k][p]);
+    }
     if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
     if (e->ev_t0[k]) cudaEventDestroy(e->ev_t0[k]);
     if (e->ev_t1[k]) cudaEventDestroy(e->ev_t1[k]);
@@ -391,8 +441,8 @@ int ssf_destroy(SsfHandle h) {
     for (void* b : own)
       if (b) cudaFree(b);
   }
-  if (e->stream2) cudaStreamDestroy(e->stream2);
-  if (e->stream3) cudaStreamDestroy(e->stream3);
+  for (int p = 1; p < SSF_SLOTS; p++)
+    if (e->stage_stream[p]) cudaStreamDestroy(e->stage_stream[p]);
   for (int g = 0; g < SSF_MAX_PEERS; g++)
     if (e->xpeer_open[g]) cudaIpcCloseMemHandle(e->xpeer_open[g]);
   void* bufs[] = {e->rgba, e->disp, e->labels, e->bound, e->inliers, e->lmap, e->in_rgb, e->in_depth, e->depth_f, e->in_depth16, e->sp, e->sums,
@@ -419,12 +469,10 @@ int ssf_set_stream(SsfHandle h, void* cuda_stream) {
   e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
   for (int k = 0; k < 2; k++)
     if (e->graph_ready[k]) { cudaGraphExecDestroy(e->graph_exec[k]); e->graph_ready[k] = false; }
-  for (int k = 0; k < SSF_SLOTS; k++) {
-    for (int b = 0; b < 2; b++)
-      if (e->ready_a[k][b]) { cudaGraphExecDestroy(e->graph_a[k][b]); e->ready_a[k][b] = false; }
-    if (e->ready_b[k]) { cudaGraphExecDestroy(e->graph_b[k]); e->ready_b[k] = false; }
-    if (e->ready_c[k]) { cudaGraphExecDestroy(e->graph_c[k]); e->ready_c[k] = false; }
-  }
+  for (int k = 0; k < SSF_SLOTS; k++)
+    for (int p = 0; p < SSF_SLOTS; p++)
+      for (int b = 0; b < 2; b++)
+        if (e->stage_ready[k][p][b]) { cudaGraphExecDestroy(e->stage_graph[k][p][b]); e->stage_ready[k][p][b] = false; }
   return SSF_OK;
 }
 
@@ -543,31 +591,25 @@ int ssf_get_filtered_depth(SsfHandle h, float* depth) {
 }
 
 // ---- pipelined mode ---------------------------------------------------------------------
-// A frame passes three stages: A (ingest + the colour-only segmentation iterations) needs only its
-// images, B (RANSAC, colour + disparity iterations, smoothing, render, extraction) needs A, and C
-// (registration + fusion) needs B and the model.  Each stage is a CUDA graph on its own stream,
-// stages of one frame are chained by events, a stage of consecutive frames is serialised by its
-// stream, and every frame owns one of three slots -- so three consecutive frames are in three
-// different stages at once.  Same kernels in the same order per frame: results are identical to the
-// synchronous path; throughput is bounded by the longest stage instead of the sum of the three.
-static int capture_stage(EngineImpl* e, cudaGraphExec_t* exec, uint64_t* launches, int stage, bool bilateral, int slot) {
+// A frame's launch sequence is a chain: ingest -> segmentation iterations -> extraction ->
+// registration + fusion.  Only the last link touches the model, so the chain of frame k+1 can run
+// behind that of frame k as soon as it keeps its own copy of the per-frame state.  The sequence is
+// cut into nb_stages contiguous stages of about equal cost; each stage is a CUDA graph on its own
+// stream, the stages of one frame are chained by events, a stage of consecutive frames is
+// serialised by its stream, and every frame in flight owns one FrameSlot.  Same kernels in the
+// same order per frame: results are identical to the synchronous path; the frame rate is set by
+// the longest stage instead of by the whole chain.
+static int capture_stage(EngineImpl* e, int slot, int stage, int gi) {
   cudaGraph_t g;
   const uint64_t before = e->launches;
   SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-  if (stage == 0) {
-    enqueue_stage_a(e, bilateral);
-  } else if (stage == 1) {
-    enqueue_stage_b(e);
-    launch_pdl(e, seg_end_kernel, dim3(1), dim3(1), 0, e->counters);
-    e->launches++;
-  } else {
-    enqueue_track(e, e->d_report2[slot], 1);
-  }
+  enqueue_steps(e, e->stage_first[stage], e->stage_first[stage + 1], gi != 0, true, e->d_report2[slot]);
   SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
-  *launches = e->launches - before;
+  e->stage_launches[slot][stage][gi] = e->launches - before;
   e->launches = before;
-  SSF_CUDA(e, cudaGraphInstantiate(exec, g, 0));
+  SSF_CUDA(e, cudaGraphInstantiate(&e->stage_graph[slot][stage][gi], g, 0));
   cudaGraphDestroy(g);
+  e->stage_ready[slot][stage][gi] = true;
   return SSF_OK;
 }
 
@@ -578,48 +620,46 @@ int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const f
   if (rgb_stride == 0) rgb_stride = (size_t)e->W * 3;
   if (depth_stride == 0) depth_stride = (size_t)e->W * 4;
   if (rgb_stride < (size_t)e->W * 3 || depth_stride < (size_t)e->W * 4) return SSF_ERR_INVALID_ARG;
-  if (e->in_flight >= SSF_SLOTS) { e->err = "three frames already in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
+  const int P = e->nb_stages;
+  if (e->in_flight >= P) { e->err = "every pipeline stage is occupied: ssf_wait_frame first"; return SSF_ERR_STATE; }
   const int s = e->pipe_next;
-  const int gi = (flags & SSF_FLAG_BILATERAL) ? 1 : 0;
   select_slot(e, s);
-  int rc = SSF_OK;
-  if (!e->ready_a[s][gi]) {
-    if ((rc = capture_stage(e, &e->graph_a[s][gi], &e->launches_a[s][gi], 0, gi != 0, s))) return rc;
-    e->ready_a[s][gi] = true;
-  }
-  if (!e->ready_b[s]) {
-    if ((rc = capture_stage(e, &e->graph_b[s], &e->launches_b[s], 1, false, s))) return rc;
-    e->ready_b[s] = true;
-  }
-  if (!e->ready_c[s]) {
-    if ((rc = capture_stage(e, &e->graph_c[s], &e->launches_c[s], 2, false, s))) return rc;
-    e->ready_c[s] = true;
+  for (int p = 0; p < P; p++) {
+    const int gi = (p == 0 && (flags & SSF_FLAG_BILATERAL)) ? 1 : 0;   // the ingest is always in stage 0
+    if (!e->stage_ready[s][p][gi]) {
+      int rc = capture_stage(e, s, p, gi);
+      if (rc) return rc;
+    }
   }
   if (e->in_flight == 0) e->pipe_oldest = s;
-  // stage A on `stream`: the slot is free once the frame that last used it has been tracked
-  SSF_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_done[s], 0));
-  SSF_CUDA(e, cudaEventRecord(e->ev_t0[s], e->stream));
-  SSF_CUDA(e, cudaMemcpy2DAsync(e->in_rgb, (size_t)e->W * 3, rgb, rgb_stride, (size_t)e->W * 3, e->H, cudaMemcpyDefault, e->stream));
-  SSF_CUDA(e, cudaMemcpy2DAsync(e->in_depth, (size_t)e->W * 4, depth, depth_stride, (size_t)e->W * 4, e->H, cudaMemcpyDefault, e->stream));
-  SSF_CUDA(e, cudaGraphLaunch(e->graph_a[s][gi], e->stream));
-  SSF_CUDA(e, cudaEventRecord(e->ev_a[s], e->stream));
-  // stage B on `stream3`
-  SSF_CUDA(e, cudaStreamWaitEvent(e->stream3, e->ev_a[s], 0));
-  SSF_CUDA(e, cudaGraphLaunch(e->graph_b[s], e->stream3));
-  SSF_CUDA(e, cudaEventRecord(e->ev_b[s], e->stream3));
-  // stage C on `stream2`
-  SSF_CUDA(e, cudaStreamWaitEvent(e->stream2, e->ev_b[s], 0));
-  if (pose_prior_Rt12) {
-    memcpy(e->h_prior2[s], pose_prior_Rt12, 12 * sizeof(float));
-    SSF_CUDA(e, cudaMemcpyAsync(e->pose, e->h_prior2[s], 12 * sizeof(float), cudaMemcpyHostToDevice, e->stream2));
+  for (int p = 0; p < P; p++) {
+    cudaStream_t st = p == 0 ? e->stream : e->stage_stream[p];
+    const int gi = (p == 0 && (flags & SSF_FLAG_BILATERAL)) ? 1 : 0;
+    if (p == 0) {
+      // the slot is free once the frame that last used it has left the last stage
+      SSF_CUDA(e, cudaStreamWaitEvent(st, e->ev_done[s], 0));
+      SSF_CUDA(e, cudaEventRecord(e->ev_t0[s], st));
+      SSF_CUDA(e, cudaMemcpy2DAsync(e->in_rgb, (size_t)e->W * 3, rgb, rgb_stride, (size_t)e->W * 3, e->H, cudaMemcpyDefault, st));
+      SSF_CUDA(e, cudaMemcpy2DAsync(e->in_depth, (size_t)e->W * 4, depth, depth_stride, (size_t)e->W * 4, e->H, cudaMemcpyDefault, st));
+    } else {
+      SSF_CUDA(e, cudaStreamWaitEvent(st, e->ev_stage[s][p - 1], 0));
+    }
+    if (p == P - 1 && pose_prior_Rt12) {
+      memcpy(e->h_prior2[s], pose_prior_Rt12, 12 * sizeof(float));
+      SSF_CUDA(e, cudaMemcpyAsync(e->pose, e->h_prior2[s], 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    SSF_CUDA(e, cudaGraphLaunch(e->stage_graph[s][p][gi], st));
+    e->launches += e->stage_launches[s][p][gi];
+    if (p < P - 1) {
+      SSF_CUDA(e, cudaEventRecord(e->ev_stage[s][p], st));
+    } else {
+      SSF_CUDA(e, cudaEventRecord(e->ev_t1[s], st));
+      SSF_CUDA(e, cudaMemcpyAsync(e->h_report2[s], e->d_report2[s], sizeof(FrameReport), cudaMemcpyDeviceToHost, st));
+      SSF_CUDA(e, cudaEventRecord(e->ev_done[s], st));
+    }
   }
-  SSF_CUDA(e, cudaGraphLaunch(e->graph_c[s], e->stream2));
-  SSF_CUDA(e, cudaEventRecord(e->ev_t1[s], e->stream2));
-  SSF_CUDA(e, cudaMemcpyAsync(e->h_report2[s], e->d_report2[s], sizeof(FrameReport), cudaMemcpyDeviceToHost, e->stream2));
-  SSF_CUDA(e, cudaEventRecord(e->ev_done[s], e->stream2));
-  e->launches += e->launches_a[s][gi] + e->launches_b[s] + e->launches_c[s];
   e->in_flight++;
-  e->pipe_next = (s + 1) % SSF_SLOTS;
+  e->pipe_next = (s + 1) % P;
   return SSF_OK;
 }
 
@@ -637,14 +677,20 @@ int ssf_wait_frame(SsfHandle h, SsfFrameStats* out, float R[9], float t[3]) {
   if (R) memcpy(R, e->h_report->pose.R, 36);
   if (t) memcpy(t, e->h_report->pose.t, 12);
   e->in_flight--;
-  e->pipe_oldest = (s + 1) % SSF_SLOTS;
+  e->pipe_oldest = (s + 1) % e->nb_stages;
   if (e->in_flight == 0) {
     // back to a quiescent state: every getter / stage entry point works on `stream` and on the
     // slot of the frame just returned
-    SSF_CUDA(e, cudaStreamSynchronize(e->stream3));
-    SSF_CUDA(e, cudaStreamSynchronize(e->stream2));
+    for (int p = 1; p < e->nb_stages; p++) SSF_CUDA(e, cudaStreamSynchronize(e->stage_stream[p]));
     select_slot(e, s);
   }
+  return SSF_OK;
+}
+
+int ssf_get_pipeline_depth(SsfHandle h, int* stages) {
+  H_CHECK(h);
+  if (!stages) return SSF_ERR_INVALID_ARG;
+  *stages = e->nb_stages;
   return SSF_OK;
 }
 

@@ -84,9 +84,9 @@ struct Counters {
 struct DevicePose { float R[9]; float t[3]; };
 
 // Everything that belongs to ONE frame on its way through the stages: the segmentation images and
-// per-superpixel state, and what segmentation + extraction hand to registration + fusion.  Three
-// sets, so that three consecutive frames can be in three different stages (ssf_submit_frame).
-constexpr int SSF_SLOTS = 3;
+// per-superpixel state, and what segmentation + extraction hand to registration + fusion.  One set
+// per pipeline stage, so that consecutive frames can be in different stages (ssf_submit_frame).
+constexpr int SSF_SLOTS = 6;          // upper bound of pipeline stages = frames in flight
 struct FrameSlot {
   uchar4* rgba;
   float* disp;
@@ -106,9 +106,10 @@ struct Engine {
   SsfConfig cfg;
   int device;
   cudaStream_t own_stream, stream;
-  cudaStream_t stream2, stream3;   // pipelined mode: registration + fusion stage, second segmentation stage
-  FrameSlot slot[SSF_SLOTS];       // slot[0] is what the synchronous entry points use
+  cudaStream_t stage_stream[SSF_SLOTS];   // pipelined mode: one stream per stage ([0] = `stream`)
+  FrameSlot slot[SSF_SLOTS];              // slot[0] is what the synchronous entry points use
   int cur_slot;
+  int nb_stages;                          // stages = frames in flight of the pipelined mode (SSF_PIPELINE_STAGES)
   cudaEvent_t ev0, ev1, evf0, evf1;
   std::string err;
   uint64_t launches;
@@ -222,7 +223,8 @@ float icp_lab_gate_sq();
 float icp_dist_gate_sq();
 void launch_ingest(Engine* e, const uint8_t* rgb_dev, size_t rgb_stride, const float* depth_dev,
                    size_t depth_stride);
-void launch_tps(Engine* e, int part = 0);
+int tps_step_count(const Engine* e);
+void launch_tps(Engine* e, int first = 0, int last = -1);   // segmentation steps [first, last)
 void launch_extract(Engine* e);
 void launch_fuse(Engine* e);
 void launch_build_lmap(Engine* e, const float* slanted_dev);

@@ -921,14 +921,18 @@ static void launch_pass(Engine* e, const TpsArgs& a, int OX, int OY) {
   e->launches += 2;
 }
 
-// part 0 = the whole segmentation; 1 = the colour-only iterations (they need nothing but the seeded
-// images); 2 = everything after them (RANSAC, colour + disparity iterations, smoothing, render).  The
-// pipelined mode runs parts 1 and 2 of consecutive frames on different streams.
-void launch_tps(Engine* e, int part) {
+// The segmentation as a sequence of steps, so that the pipelined mode can cut it anywhere between
+// two iterations: steps [0, I/2) are the colour-only iterations, step I/2 is the disparity-plane
+// initialisation (RANSAC + inlier moments + merge), steps (I/2, I] the colour + disparity
+// iterations, step I + 1 smoothing + render.  launch_tps(e, first, last) enqueues steps [first, last).
+int tps_step_count(const Engine* e) { return e->tps_persistent ? 1 : e->cfg.seg_iter + 2; }
+
+void launch_tps(Engine* e, int first, int last) {
   TpsArgs a = tps_args(e);
   const int nbIters = e->cfg.seg_iter;
+  if (last < 0) last = tps_step_count(e);
   if (e->tps_persistent) {
-    if (part == 1) return;             // the one-kernel form is not split: it runs as part 2
+    if (first > 0 || last < 1) return;      // the one-kernel form is a single step
     TpsRun r;
     r.nb_iters = nbIters; r.use_ransac = e->cfg.seg_use_ransac; r.nb_samples = e->cfg.nb_samples;
     r.filter_iters = e->cfg.filter_iter;
@@ -949,40 +953,41 @@ void launch_tps(Engine* e, int part) {
     e->launches++;
     return;
   }
-  if (part != 2) {
-    for (int k = 0; k < nbIters / 2; k++) {
+  const int half = nbIters / 2;
+  dim3 blk(32, 8), grd(cdiv(e->W, 32), cdiv(e->H, 8));
+  for (int step = first; step < last; step++) {
+    if (step < half) {                       // colour-only iteration
       launch_pass<false>(e, a, 0, 0);
       launch_pass<false>(e, a, 1, 1);
       launch_pass<false>(e, a, 0, 1);
       launch_pass<false>(e, a, 1, 0);
+    } else if (step == half) {               // disparity planes: RANSAC, inlier moments, first merge
+      if (e->cfg.seg_use_ransac) {
+        int* votes = reinterpret_cast<int*>(e->samples + (size_t)e->S * e->cfg.nb_samples);
+        launch_pdl(e, tps_init_samples_kernel, dim3(e->S), dim3(e->cfg.nb_samples), 0,
+            a, e->samples, votes, reinterpret_cast<curandState*>(e->rng), 10, (float)e->cfg.cell_size / 2.f);
+        launch_pdl(e, tps_eval_samples_kernel, dim3(grd), dim3(blk), 0, a, e->samples, votes, e->cfg.nb_samples);
+        launch_pdl(e, tps_select_samples_kernel, dim3(cdiv(e->S, 128)), dim3(128), 0, a, e->samples, votes, e->cfg.nb_samples);
+        launch_pdl(e, tps_init_disp_kernel, dim3(grd), dim3(blk), 0, a, 1);
+        e->launches += 4;
+      } else {
+        launch_pdl(e, tps_init_disp_kernel, dim3(grd), dim3(blk), 0, a, 0);
+        e->launches += 1;
+      }
+      launch_pdl(e, tps_merge_kernel<true>, dim3(cdiv(a.S, 128)), dim3(128), 0, a);
+      e->launches++;
+    } else if (step <= nbIters) {            // colour + disparity iteration
+      launch_pass<true>(e, a, 0, 0);
+      launch_pass<true>(e, a, 1, 1);
+      launch_pass<true>(e, a, 0, 1);
+      launch_pass<true>(e, a, 1, 0);
+    } else {                                 // plane smoothing + slanted-depth render
+      launch_pdl(e, tps_filter_kernel, dim3(1), dim3(1024), 0, a, e->filt_a, e->filt_b, e->cfg.filter_iter, e->cfg.filter_alpha,
+                                                   e->cfg.filter_beta, e->cfg.filter_threshold);
+      launch_pdl(e, tps_render_kernel, dim3(grd), dim3(blk), 0, a, e->lmap);
+      e->launches += 2;
     }
   }
-  if (part == 1) return;
-  dim3 blk(32, 8), grd(cdiv(e->W, 32), cdiv(e->H, 8));
-  if (e->cfg.seg_use_ransac) {
-    int* votes = reinterpret_cast<int*>(e->samples + (size_t)e->S * e->cfg.nb_samples);
-    launch_pdl(e, tps_init_samples_kernel, dim3(e->S), dim3(e->cfg.nb_samples), 0, 
-        a, e->samples, votes, reinterpret_cast<curandState*>(e->rng), 10, (float)e->cfg.cell_size / 2.f);
-    launch_pdl(e, tps_eval_samples_kernel, dim3(grd), dim3(blk), 0, a, e->samples, votes, e->cfg.nb_samples);
-    launch_pdl(e, tps_select_samples_kernel, dim3(cdiv(e->S, 128)), dim3(128), 0, a, e->samples, votes, e->cfg.nb_samples);
-    launch_pdl(e, tps_init_disp_kernel, dim3(grd), dim3(blk), 0, a, 1);
-    e->launches += 4;
-  } else {
-    launch_pdl(e, tps_init_disp_kernel, dim3(grd), dim3(blk), 0, a, 0);
-    e->launches += 1;
-  }
-  launch_pdl(e, tps_merge_kernel<true>, dim3(cdiv(a.S, 128)), dim3(128), 0, a);
-  e->launches++;
-  for (int k = nbIters / 2; k < nbIters; k++) {
-    launch_pass<true>(e, a, 0, 0);
-    launch_pass<true>(e, a, 1, 1);
-    launch_pass<true>(e, a, 0, 1);
-    launch_pass<true>(e, a, 1, 0);
-  }
-  launch_pdl(e, tps_filter_kernel, dim3(1), dim3(1024), 0, a, e->filt_a, e->filt_b, e->cfg.filter_iter, e->cfg.filter_alpha,
-                                               e->cfg.filter_beta, e->cfg.filter_threshold);
-  launch_pdl(e, tps_render_kernel, dim3(grd), dim3(blk), 0, a, e->lmap);
-  e->launches += 2;
 }
 
 }  // namespace ssf

@@ -64,7 +64,7 @@ SSF_FLAG_BILATERAL = 1   # include/ssf.h
 EXPORTS = [
     "ssf_config_default", "ssf_create", "ssf_destroy", "ssf_set_stream", "ssf_last_error", "ssf_is_initialized",
     "ssf_process_frame", "ssf_process_frame_depth16", "ssf_process_frame_device", "ssf_bilateral_filter",
-    "ssf_get_filtered_depth", "ssf_get_gray", "ssf_get_frame_stats", "ssf_submit_frame", "ssf_wait_frame", "ssf_get_pose", "ssf_set_pose",
+    "ssf_get_filtered_depth", "ssf_get_gray", "ssf_get_frame_stats", "ssf_submit_frame", "ssf_wait_frame", "ssf_get_pipeline_depth", "ssf_get_pose", "ssf_set_pose",
     "ssf_get_stamp", "ssf_set_stamp", "ssf_get_counts", "ssf_get_nb_superpixels", "ssf_copy_model",
     "ssf_copy_frame", "ssf_get_segmentation", "ssf_render_preview", "ssf_get_slanted_depth", "ssf_export_model",
     "ssf_extract_local_point_cloud", "ssf_invalidate_frame_supersurfels", "ssf_transform_model", "ssf_set_model",
@@ -305,6 +305,12 @@ class SupersurfelFusion:
             prior = np.concatenate([np.asarray(R, np.float32).reshape(9), np.asarray(t, np.float32).reshape(3)])
         rc = self._lib.ssf_submit_frame(self._h, _ptr(rgb), self.width * 3, _ptr(depth), self.width * 4, _ptr(prior), flags)
         self._check(rc, "ssf_submit_frame")
+
+    def pipelineDepth(self):
+        """Frames that may be in flight through submitFrame (= pipeline stages)."""
+        n = C.c_int(0)
+        self._check(self._lib.ssf_get_pipeline_depth(self._h, C.byref(n)), "ssf_get_pipeline_depth")
+        return n.value
 
     def waitFrame(self):
         """Blocks until the oldest submitted frame is done; returns (stats, R, t)."""

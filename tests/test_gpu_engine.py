@@ -143,28 +143,34 @@ def test_export_model_format(orc, tmp_path):
     assert np.array_equal(geng.computeSlantedPlaneIm(), geng.getSegmentation()["slanted"], equal_nan=True)
 
 
-def test_pipelined_frames_equal_synchronous_frames(orc):
-    """ssf_submit_frame / ssf_wait_frame (three frames in flight, one per stage, on three streams) must give
-    bit-identical stats, poses and models to ssf_process_frame."""
+@pytest.mark.parametrize("stages", ["1", "2", "4", "6"])
+def test_pipelined_frames_equal_synchronous_frames(orc, monkeypatch, stages):
+    """ssf_submit_frame / ssf_wait_frame (the frame's kernel chain cut into stages on separate streams, one
+    frame in flight per stage) must give bit-identical stats, poses and models to ssf_process_frame."""
     from supersurfel_fusion_b200 import CamParam, SupersurfelFusion
+    from supersurfel_fusion_b200.engine import SSF_FLAG_BILATERAL
+    monkeypatch.setenv("SSF_PIPELINE_STAGES", stages)
     seq = SyntheticSequence(width=320, height=240, seed=31)
     cam = CamParam(*seq.cam_param())
     params = dict(TUM_PARAMS, nb_supersurfels_max=20000)
-    frames = [seq.frame(k) for k in range(12)]
+    frames = [seq.frame(k) for k in range(14)]
+    flags = SSF_FLAG_BILATERAL if stages == "4" else 0
     sync = SupersurfelFusion().initialize(cam, **params)
     want = []
     for rgb, depth in frames:
-        st = sync.processFrame(rgb, depth)
+        st = sync.processFrame(rgb, depth, flags=flags)
         want.append((st, sync.getPose()))
     pipe = SupersurfelFusion().initialize(cam, **params)
+    depth_p = pipe.pipelineDepth()
+    assert depth_p == int(stages)
     got = []
-    pipe.submitFrame(*frames[0])
-    pipe.submitFrame(*frames[1])
-    for k in range(2, len(frames)):
-        pipe.submitFrame(*frames[k])          # frame k enters while frames k-1 and k-2 are still in later stages
+    for k in range(len(frames)):
+        if k >= depth_p:
+            got.append(pipe.waitFrame())      # keep `depth_p` frames in flight
+        pipe.submitFrame(*frames[k], flags=flags)
+    for _ in range(min(depth_p, len(frames))):
         got.append(pipe.waitFrame())
-    got.append(pipe.waitFrame())
-    got.append(pipe.waitFrame())
+    assert len(got) == len(want)
     for k, ((st_w, (R_w, t_w)), (st_g, R_g, t_g)) in enumerate(zip(want, got)):
         for key in ("stamp", "nb_supersurfels", "nb_visible", "nb_removed", "nb_matched", "nb_inserted", "icp_valid", "icp_iters"):
             assert st_g[key] == st_w[key], (k, key, st_g, st_w)
@@ -174,12 +180,15 @@ def test_pipelined_frames_equal_synchronous_frames(orc):
     assert np.array_equal(ms.positions, mp.positions) and np.array_equal(ms.confidences, mp.confidences)
     assert np.array_equal(ms.stamps, mp.stamps)
     assert np.array_equal(sync.getSegmentation()["labels"], pipe.getSegmentation()["labels"])
-    # a fourth frame in flight, and a synchronous call while frames are in flight, are refused
-    pipe.submitFrame(*frames[0]); pipe.submitFrame(*frames[1]); pipe.submitFrame(*frames[2])
+    assert np.array_equal(sync.getFrame().positions, pipe.getFrame().positions)
+    # one frame too many in flight, and a synchronous call while frames are in flight, are refused
+    for k in range(depth_p):
+        pipe.submitFrame(*frames[k])
     with pytest.raises(Exception):
-        pipe.submitFrame(*frames[3])
+        pipe.submitFrame(*frames[depth_p])
     with pytest.raises(Exception):
         pipe.processFrame(*frames[2])
-    pipe.waitFrame(); pipe.waitFrame(); pipe.waitFrame()
+    for _ in range(depth_p):
+        pipe.waitFrame()
     pipe.processFrame(*frames[2])             # and it works again once the pipeline has drained
     sync.close(); pipe.close()

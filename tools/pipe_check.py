@@ -18,13 +18,13 @@ def run(bufs, pipelined, steps=300):
         eng.processFrame(*bufs[bench.frame_index(s)])
     t0 = time.perf_counter()
     if pipelined:
-        eng.submitFrame(*bufs[bench.frame_index(10)])
-        eng.submitFrame(*bufs[bench.frame_index(11)])
-        for s in range(12, 10 + steps):
+        depth = eng.pipelineDepth()
+        for s in range(10, 10 + steps):
+            if s - 10 >= depth:
+                eng.waitFrame()
             eng.submitFrame(*bufs[bench.frame_index(s)])
+        for _ in range(depth):
             eng.waitFrame()
-        eng.waitFrame()
-        eng.waitFrame()
     else:
         for s in range(10, 10 + steps):
             eng.processFrame(*bufs[bench.frame_index(s)])
@@ -32,5 +32,6 @@ def run(bufs, pipelined, steps=300):
     st = eng.getFrameStats()
     eng.close()
     return steps / dt, st["nb_supersurfels"]
+print("stages", os.environ.get("SSF_PIPELINE_STAGES", "default"))
 for name, bufs in (("device", d), ("pinned-host", hp)):
     print(name, "sync", run(bufs, False), "pipelined", run(bufs, True))
