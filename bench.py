@@ -433,7 +433,7 @@ def run_ours(args, rank, world, local_rank):
                                 "ssf_process_frame, whose numbers are under 'synchronous'" % pipe_depth) if pipelined
                                else "synchronous ssf_process_frame, one frame at a time",
                    "timing": "CUDA events on the engine stream around all K frames (pipeline drained inside), max over ranks"},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": SIZE[0] * SIZE[1] * 7, "d2h_bytes_per_step": 104,
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": SIZE[0] * SIZE[1] * 7, "d2h_bytes_per_step": 112,
                 "ms_per_step": ms_e / args.steps, "wall_ms_per_step": wall_e / args.steps},
         "wall_ms_per_step": wall_ms / args.steps,
         "synchronous": None if sync_ms is None else {
