@@ -152,7 +152,9 @@ int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out);
  * same order per frame: results are identical to ssf_process_frame; latency per frame is
  * unchanged, the frame rate is set by the longest stage.  The input buffers must stay valid until
  * the frame has been waited for (pinned host memory or device memory for a truly asynchronous
- * copy).  The synchronous entry points and the getters require that no frame is in flight. */
+ * copy).  The synchronous entry points and the getters require that no frame is in flight; a
+ * caller that must edit the frame between stages (ssf_invalidate_frame_supersurfels, the MOD
+ * hook) drives the stage entry points below instead. */
 int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth,
                      size_t depth_stride, const float* pose_prior_Rt12, uint32_t flags);
 int ssf_wait_frame(SsfHandle h, SsfFrameStats* out, float R[9], float t[3]);

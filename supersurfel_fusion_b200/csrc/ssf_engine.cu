@@ -465,6 +465,7 @@ int ssf_destroy(SsfHandle h) {
 
 int ssf_set_stream(SsfHandle h, void* cuda_stream) {
   H_CHECK(h);
+  if (e->in_flight) { e->err = "pipelined frames in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
   for (int k = 0; k < 2; k++)
