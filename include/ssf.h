@@ -185,6 +185,20 @@ int ssf_get_nb_superpixels(SsfHandle h, int* nb_superpixels);
  * (node/supersurfel_fusion_node.cpp:306-310). */
 int ssf_copy_model(SsfHandle h, const SsfSurfels* dst, int n);
 int ssf_copy_frame(SsfHandle h, const SsfSurfels* dst);
+/* getModel() / getFrame() without a copy, for consumers that live on the same GPU: the engine's
+ * own planar storage.  Plane p of element i is base[p * stride + i]; planes: 0-2 position,
+ * 3-5 colour (RGB 0..255), 6-7 stamps (int32 bit patterns), 8-16 orientation (rows e1, e2,
+ * normal), 17-22 shape (xx xy xz yy yz zz), 23-24 dims, 25 confidence, 26-28 CIELab of the colour.
+ * count = nb_supersurfels (model) or the number of superpixels (frame).  Read-only; valid until
+ * the next frame is processed. */
+typedef struct SsfPlanarView {
+  const float* base;   /* device pointer */
+  int stride;          /* elements per plane */
+  int count;           /* valid elements */
+  int planes;          /* 29 */
+} SsfPlanarView;
+int ssf_get_model_view(SsfHandle h, SsfPlanarView* out);
+int ssf_get_frame_view(SsfHandle h, SsfPlanarView* out);
 /* tps->getIndexImage() / getBoundaryImage() / getInliersImage() / getDispImage()
  * (TPS_RGBD.hpp:77-81), the slanted-plane depth (computeDepthImage, TPS_RGBD.cu:507-525)
  * and tps->getSuperpixels() as S x 12 floats (TPS_RGBD.hpp:33-38).  NULL = skip. */

@@ -833,6 +833,29 @@ int ssf_render_preview(SsfHandle h, uint8_t* bgr) {
   return SSF_OK;
 }
 
+int ssf_get_model_view(SsfHandle h, SsfPlanarView* out) {
+  H_CHECK(h);
+  if (!out) return SSF_ERR_INVALID_ARG;
+  int rc = read_report(e, false);
+  if (rc) return rc;
+  out->base = e->model.base;
+  out->stride = e->model.stride;
+  out->count = e->h_report->counters.nb_supersurfels;
+  out->planes = P_COUNT;
+  return SSF_OK;
+}
+
+int ssf_get_frame_view(SsfHandle h, SsfPlanarView* out) {
+  H_CHECK(h);
+  if (!out) return SSF_ERR_INVALID_ARG;
+  if (e->in_flight) { e->err = "pipelined frames in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
+  out->base = e->frame.base;
+  out->stride = e->frame.stride;
+  out->count = e->S;
+  out->planes = P_COUNT;
+  return SSF_OK;
+}
+
 int ssf_export_model(SsfHandle h, const char* path) {
   H_CHECK(h);
   if (!path) return SSF_ERR_INVALID_ARG;

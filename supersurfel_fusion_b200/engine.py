@@ -51,6 +51,10 @@ class SsfSurfels(C.Structure):
                 ("confidences", C.c_void_p)]
 
 
+class SsfPlanarView(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("stride", C.c_int), ("count", C.c_int), ("planes", C.c_int)]
+
+
 class SsfFrameStats(C.Structure):
     _fields_ = [("stamp", C.c_int32), ("nb_supersurfels", C.c_int32), ("nb_visible", C.c_int32),
                 ("nb_removed", C.c_int32), ("nb_matched", C.c_int32), ("nb_inserted", C.c_int32),
@@ -64,7 +68,7 @@ SSF_FLAG_BILATERAL = 1   # include/ssf.h
 EXPORTS = [
     "ssf_config_default", "ssf_create", "ssf_destroy", "ssf_set_stream", "ssf_last_error", "ssf_is_initialized",
     "ssf_process_frame", "ssf_process_frame_depth16", "ssf_process_frame_device", "ssf_bilateral_filter",
-    "ssf_get_filtered_depth", "ssf_get_gray", "ssf_get_frame_stats", "ssf_submit_frame", "ssf_wait_frame", "ssf_get_pipeline_depth", "ssf_get_pose", "ssf_set_pose",
+    "ssf_get_filtered_depth", "ssf_get_gray", "ssf_get_frame_stats", "ssf_submit_frame", "ssf_wait_frame", "ssf_get_pipeline_depth", "ssf_get_model_view", "ssf_get_frame_view", "ssf_get_pose", "ssf_set_pose",
     "ssf_get_stamp", "ssf_set_stamp", "ssf_get_counts", "ssf_get_nb_superpixels", "ssf_copy_model",
     "ssf_copy_frame", "ssf_get_segmentation", "ssf_render_preview", "ssf_get_slanted_depth", "ssf_export_model",
     "ssf_extract_local_point_cloud", "ssf_invalidate_frame_supersurfels", "ssf_transform_model", "ssf_set_model",
@@ -368,6 +372,17 @@ class SupersurfelFusion:
         v = m.view()
         self._check(self._lib.ssf_copy_model(self._h, C.byref(v), n), "ssf_copy_model")
         return m
+
+    def getModelView(self):
+        """getModel() without a copy: (device pointer, stride, count, planes) of the planar model storage."""
+        v = SsfPlanarView()
+        self._check(self._lib.ssf_get_model_view(self._h, C.byref(v)), "ssf_get_model_view")
+        return v.base, v.stride, v.count, v.planes
+
+    def getFrameView(self):
+        v = SsfPlanarView()
+        self._check(self._lib.ssf_get_frame_view(self._h, C.byref(v)), "ssf_get_frame_view")
+        return v.base, v.stride, v.count, v.planes
 
     def getFrame(self):
         f = Supersurfels(self.nbSuperpixels)

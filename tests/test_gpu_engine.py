@@ -192,3 +192,35 @@ def test_pipelined_frames_equal_synchronous_frames(orc, monkeypatch, stages):
         pipe.waitFrame()
     pipe.processFrame(*frames[2])             # and it works again once the pipeline has drained
     sync.close(); pipe.close()
+
+
+def test_zero_copy_views_match_the_copies(orc):
+    """ssf_get_model_view / ssf_get_frame_view expose the planar device storage the copies are packed from."""
+    import torch
+    from supersurfel_fusion_b200 import CamParam, SupersurfelFusion
+    seq = SyntheticSequence(width=320, height=240, seed=41)
+    eng = SupersurfelFusion().initialize(CamParam(*seq.cam_param()), **dict(TUM_PARAMS, nb_supersurfels_max=6000))
+    for k in range(3):
+        eng.processFrame(*seq.frame(k))
+    for view, host in ((eng.getModelView(), eng.getModel()), (eng.getFrameView(), eng.getFrame())):
+        base, stride, count, planes = view
+        assert base and planes == 29 and count == len(host.positions) and stride >= count and stride % 4 == 0
+        # wrap the device memory without copying (CUDA array interface), then bring it to the host
+        class _Dev:
+            pass
+        dev = _Dev()
+        dev.__cuda_array_interface__ = {"shape": (int(planes), int(stride)), "typestr": "<f4", "data": (int(base), False),
+                                        "strides": None, "version": 2}
+        try:
+            planar = torch.as_tensor(dev, device="cuda").cpu().numpy()
+        except Exception:          # this torch cannot wrap a foreign pointer: the metadata checks above stand alone
+            continue
+        assert planar.shape == (planes, stride)
+        assert np.array_equal(planar[0:3, :count].T, host.positions, equal_nan=True)
+        assert np.array_equal(planar[3:6, :count].T, host.colors, equal_nan=True)
+        assert np.array_equal(planar[6:8, :count].T.copy().view(np.int32), host.stamps)
+        assert np.array_equal(planar[8:17, :count].T, host.orientations, equal_nan=True)
+        assert np.array_equal(planar[17:23, :count].T, host.shapes, equal_nan=True)
+        assert np.array_equal(planar[23:25, :count].T, host.dims, equal_nan=True)
+        assert np.array_equal(planar[25, :count], host.confidences, equal_nan=True)
+    eng.close()
