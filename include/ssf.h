@@ -159,6 +159,12 @@ int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const f
                      size_t depth_stride, const float* pose_prior_Rt12, uint32_t flags);
 int ssf_wait_frame(SsfHandle h, SsfFrameStats* out, float R[9], float t[3]);
 int ssf_get_pipeline_depth(SsfHandle h, int* stages);
+/* How a configuration's frame is cut into pipeline stages (no device needed): the frame is the
+ * step sequence 0 = ingest, 1 .. T = segmentation steps (T = seg_iter + 2: colour iterations,
+ * disparity-plane initialisation, colour + disparity iterations, smoothing + render), T + 1 =
+ * extraction, T + 2 = registration + fusion; stage p runs steps [first[p], first[p + 1]).
+ * first must hold stages + 1 ints.  Returns the number of stages used (>= 1), *nb_steps = T + 3. */
+int ssf_plan_pipeline(const SsfConfig* cfg, int stages, int persistent_segmentation, int* first, int* nb_steps);
 
 /* ---- ingest (supersurfel_fusion.cu:171-181) -------------------------------- */
 /* cv::cuda::bilateralFilter(depth, depth, kernel_size, sigma_color, sigma_spatial)

@@ -130,25 +130,31 @@ static void enqueue_steps(EngineImpl* e, int g0, int g1, bool bilateral, bool pi
   if (g0 <= T + 2 && g1 > T + 2) enqueue_track(e, report, pipelined ? 1 : 3);
 }
 
-// Cut the steps into `stages` contiguous groups minimising the heaviest group (weights ~ kernel
-// launches of a step, the quantity that sets a stage's duration at VGA).
-static void plan_stages(EngineImpl* e, int stages) {
-  const int G = frame_step_count(e), T = tps_step_count(e), half = e->cfg.seg_iter / 2;
+// Cut the frame's steps (0 = ingest, 1 .. T = segmentation steps, T + 1 = extraction, T + 2 =
+// registration + fusion) into `stages` contiguous groups minimising the heaviest group; weights ~
+// kernel launches of a step, the quantity that sets a stage's duration at VGA.  Pure function of
+// the configuration (also behind ssf_plan_pipeline for the CPU tests); writes first[0 .. used]
+// and returns the number of stages used.
+static int plan_stages_impl(int seg_iter, int icp_iter, int persistent, int stages, int* first) {
+  const int T = persistent ? 1 : seg_iter + 2, G = T + 3, half = seg_iter / 2;
+  if (stages < 1) stages = 1;
+  if (stages > SSF_SLOTS) stages = SSF_SLOTS;
+  if (stages > G) stages = G;
+  if (G > 64) { first[0] = 0; first[1] = G; return 1; }      // absurd iteration counts: no pipelining
   int w[64];
   for (int g = 0; g < G; g++) {
     if (g == 0) w[g] = 3;
     else if (g <= T) {
       const int t = g - 1;
-      w[g] = e->tps_persistent ? 60 : (t < half ? 8 : (t == half ? 6 : (t <= e->cfg.seg_iter ? 10 : 3)));
+      w[g] = persistent ? 60 : (t < half ? 8 : (t == half ? 6 : (t <= seg_iter ? 10 : 3)));
     } else if (g == T + 1) w[g] = 3;
-    else w[g] = 12 + e->cfg.icp_iter;
+    else w[g] = 12 + icp_iter;
   }
-  if (stages > G) stages = G;
   // dynamic programme: best[p][g] = minimal heaviest group when the first g steps form p groups
   static const int INF = 1 << 28;
   int best[SSF_SLOTS + 1][65], cut[SSF_SLOTS + 1][65];
   for (int p = 0; p <= stages; p++)
-    for (int g = 0; g <= G; g++) best[p][g] = INF;
+    for (int g = 0; g <= G; g++) { best[p][g] = INF; cut[p][g] = 0; }
   best[0][0] = 0;
   for (int p = 1; p <= stages; p++)
     for (int g = p; g <= G; g++) {
@@ -159,10 +165,14 @@ static void plan_stages(EngineImpl* e, int stages) {
         if (cand < best[p][g]) { best[p][g] = cand; cut[p][g] = k; }
       }
     }
-  e->nb_stages = stages;
   int g = G;
-  for (int p = stages; p >= 1; p--) { e->stage_first[p] = g; g = cut[p][g]; }
-  e->stage_first[0] = 0;
+  for (int p = stages; p >= 1; p--) { first[p] = g; g = cut[p][g]; }
+  first[0] = 0;
+  return stages;
+}
+
+static void plan_stages(EngineImpl* e, int stages) {
+  e->nb_stages = plan_stages_impl(e->cfg.seg_iter, e->cfg.icp_iter, e->tps_persistent, stages, e->stage_first);
 }
 
 static void enqueue_seg(EngineImpl* e, bool bilateral) {
@@ -686,6 +696,13 @@ int ssf_wait_frame(SsfHandle h, SsfFrameStats* out, float R[9], float t[3]) {
     select_slot(e, s);
   }
   return SSF_OK;
+}
+
+int ssf_plan_pipeline(const SsfConfig* cfg, int stages, int persistent_segmentation, int* first, int* nb_steps) {
+  if (!cfg || !first) return SSF_ERR_INVALID_ARG;
+  const int used = plan_stages_impl(cfg->seg_iter, cfg->icp_iter, persistent_segmentation, stages, first);
+  if (nb_steps) *nb_steps = (persistent_segmentation ? 1 : cfg->seg_iter + 2) + 3;
+  return used;
 }
 
 int ssf_get_pipeline_depth(SsfHandle h, int* stages) {
