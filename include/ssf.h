@@ -52,8 +52,13 @@ typedef struct SsfCamParam {
 /* The hot-path arguments of SupersurfelFusion::initialize
  * (supersurfel_fusion.hpp:46-74), same names, same defaults.  The sparse-VO
  * arguments (nb_features ... untracked_threshold) belong to an out-of-scope
- * neighbour and are not part of this struct; enable_loop_closure / enable_mod are
- * accepted for signature compatibility and must be 0. */
+ * neighbour and are not part of this struct.  enable_loop_closure / enable_mod keep the
+ * reference's defaults (true, supersurfel_fusion.hpp:72-73) and are RECORDED, not acted on:
+ * the ferns loop detector + deformation-graph optimisation and the MOD / YOLO detector are
+ * out-of-scope neighbours of this path.  A caller that runs them feeds their results in
+ * through the hooks below (ssf_invalidate_frame_supersurfels, ssf_align, ssf_apply_deformation,
+ * ssf_set_pose, ssf_transform_model); with no caller driving the hooks the library behaves as
+ * the reference does with both switches off. */
 typedef struct SsfConfig {
   SsfCamParam cam;
   int cell_size;          /* 16 */
@@ -76,8 +81,8 @@ typedef struct SsfConfig {
   int nb_supersurfels_max;/* 50000 */
   int icp_iter;           /* 10 */
   double icp_cov_thresh;  /* 0.04 */
-  int enable_loop_closure;/* must be 0 */
-  int enable_mod;         /* must be 0 */
+  int enable_loop_closure;/* 1 (recorded; see above) */
+  int enable_mod;         /* 1 (recorded; see above) */
 } SsfConfig;
 
 /* Host-or-device view of supersurfel arrays (any member may be NULL = skip). */
@@ -106,6 +111,15 @@ typedef struct SsfFrameStats {
   float icp_inliers;
   double icp_error;         /* sqrt(r / inliers) of the last built system */
   float gpu_ms;             /* device time of the frame (CUDA events) */
+  /* Per-stage device times, the breakdown the reference prints per frame
+   * (supersurfel_fusion.cu:516-528); filled by the synchronous entry points when
+   * SSF_FLAG_STAGE_TIMING is set (event nodes at the stage boundaries of the frame graph), else 0.
+   * Not available in pipelined mode, where the stages of consecutive frames overlap. */
+  float ms_ingest;          /* [bilateral filter,] RGBA / disparity conversion, grid seeding */
+  float ms_segmentation;    /* tps->compute + filter + computeDepthImage */
+  float ms_extraction;      /* generateSupersurfels */
+  float ms_registration;    /* featureConstrainedSymmetricICP + pose composition */
+  float ms_fusion;          /* association, update, insert, cull + partition */
 } SsfFrameStats;
 
 /* ---- lifecycle ----------------------------------------------------------- */
@@ -130,6 +144,7 @@ int ssf_is_initialized(SsfHandle h);
  * previous fused pose.  Depth is expected already bilateral-filtered unless
  * SSF_FLAG_BILATERAL is set.  Synchronous, like the reference. */
 #define SSF_FLAG_BILATERAL 1u
+#define SSF_FLAG_STAGE_TIMING 2u /* fill SsfFrameStats.ms_* (synchronous entry points only) */
 int ssf_process_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth,
                       size_t depth_stride, const float* pose_prior_Rt12, uint32_t flags);
 /* Same with the 16-bit depth image of the TUM / live drivers: decodes
@@ -154,7 +169,19 @@ int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out);
  * the frame has been waited for (pinned host memory or device memory for a truly asynchronous
  * copy).  The synchronous entry points and the getters require that no frame is in flight; a
  * caller that must edit the frame between stages (ssf_invalidate_frame_supersurfels, the MOD
- * hook) drives the stage entry points below instead. */
+ * hook) drives the stage entry points below instead.
+ * Pose priors: a prior given to ssf_submit_frame is fixed at submit time, i.e. BEFORE the up to
+ * depth-1 older frames in flight have been fused -- it cannot be derived from the previous
+ * frame's fused pose (an external odometry source that runs ahead of the fusion is fine; NULL,
+ * "keep the previous fused pose", is always exact because the last stage reads the pose on the
+ * device).  A visual-odometry front end that needs frame k's fused pose to predict frame k+1
+ * must use the synchronous ssf_process_frame.
+ * Error handling: if a submit fails after part of the frame was enqueued the handle is retired
+ * (every later call returns SSF_ERR_STATE; ssf_last_error tells why); destroy and re-create it.
+ * ssf_prepare() builds and uploads every CUDA graph the given flags need (synchronous frame
+ * graph and all slot x stage graphs) so that the first frames do not pay for stream capture and
+ * graph instantiation; without it the graphs are built lazily by the first calls. */
+int ssf_prepare(SsfHandle h, uint32_t flags);
 int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth,
                      size_t depth_stride, const float* pose_prior_Rt12, uint32_t flags);
 int ssf_wait_frame(SsfHandle h, SsfFrameStats* out, float R[9], float t[3]);

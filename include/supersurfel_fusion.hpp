@@ -51,7 +51,8 @@ class SupersurfelFusion {
   SupersurfelFusion(const SupersurfelFusion&) = delete;
   SupersurfelFusion& operator=(const SupersurfelFusion&) = delete;
 
-  // supersurfel_fusion.hpp:46-74 -- same order, names and defaults
+  // supersurfel_fusion.hpp:46-74 -- same order, names and defaults.  enable_loop_closure / enable_mod
+  // are recorded only: the loop detector and MOD are the caller's, see the note in ssf.h (SsfConfig).
   void initialize(const CamParam& cam_param, int cell_size = 16, float lambda_pos = 50.0f,
                   float lambda_bound = 1000.0f, float lambda_size = 10000.0f, float lambda_disp = 1000000.0f,
                   float thresh_disp = 0.0001f, int seg_iter = 10, bool seg_use_ransac = true, int nb_samples = 16,
@@ -60,7 +61,7 @@ class SupersurfelFusion {
                   float conf_thresh = 2500.0f, int nb_supersurfels_max = 50000, int icp_iter = 10,
                   double icp_cov_thresh = 0.04, int /*nb_features*/ = 2000, float /*features_scale_factor*/ = 1.2f,
                   int /*features_nb_levels*/ = 8, int /*ini_th_fast*/ = 20, int /*min_th_fast*/ = 7,
-                  int /*untracked_threshold*/ = 10, bool enable_loop_closure = false, bool enable_mod = false) {
+                  int /*untracked_threshold*/ = 10, bool enable_loop_closure = true, bool enable_mod = true) {
     SsfConfig c;
     ssf_config_default(&c);
     c.cam = SsfCamParam{cam_param.fx, cam_param.fy, cam_param.cx, cam_param.cy, cam_param.height, cam_param.width};

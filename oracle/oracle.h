@@ -86,7 +86,13 @@ void orc_generate_supersurfels(const OrcCam* cam, int n_superpixels, const uint8
                                float z_min, float z_max, int stamp, OrcSurfels* frame);
 
 /* ---- fusion (supersurfel_fusion.cu:351-483, supersurfel_fusion_kernels.cu:348-467,522-682) */
-typedef struct OrcFuseCounts { int nb_supersurfels, nb_visible, nb_removed, nb_matched, nb_inserted; } OrcFuseCounts;
+typedef struct OrcFuseCounts {
+  int nb_supersurfels, nb_visible, nb_removed, nb_matched, nb_inserted;
+  /* why filterModel removed them (supersurfel_fusion_kernels.cu:429-449), a split of nb_removed for the tests:
+   * stale = (age > delta_t && conf < conf_thresh && stamp > delta_t), invalid = conf <= 0 only,
+   * occluded = in view and in front of the slanted depth (p.z < 0.8 z) */
+  int nb_removed_stale, nb_removed_invalid, nb_removed_occluded;
+} OrcFuseCounts;
 /* model arrays have capacity nb_max; counts in/out. */
 void orc_fuse(const OrcCam* cam, int n_superpixels, const OrcSurfels* frame, OrcSurfels* model,
               int nb_max, const float* R9, const float* t3, const int32_t* labels,
@@ -114,13 +120,24 @@ typedef struct OrcFrameStats {
   int icp_ran, icp_valid, icp_iters;
   float icp_inliers;
   double icp_error;
+  int nb_matched, nb_inserted, nb_removed_stale, nb_removed_invalid, nb_removed_occluded;
 } OrcFrameStats;
 OrcEngine* orc_engine_create(const OrcConfig* cfg);
 void orc_engine_destroy(OrcEngine*);
 /* prior_Rt12: optional pose prior (R row-major 9 + t 3), NULL = previous pose. */
 void orc_engine_process_frame(OrcEngine*, const uint8_t* rgb, const float* depth, const float* prior_Rt12,
                               OrcFrameStats* stats);
+/* Same with the MOD hook: mask[S] != 0 marks a frame supersurfel dynamic -> confidence = -1 right after
+ * generateSupersurfels and before the registration, where the reference's detectMotion writes
+ * frame.confidences (supersurfel_fusion.cu:194-213, motion_detection.cu:573).  mask may be NULL. */
+void orc_engine_process_frame_masked(OrcEngine*, const uint8_t* rgb, const float* depth, const float* prior_Rt12,
+                                     const uint8_t* mask, OrcFrameStats* stats);
 void orc_engine_get_pose(const OrcEngine*, float* R9, float* t3);
+void orc_engine_set_pose(OrcEngine*, const float* R9, const float* t3);
+/* applyTransformSuperSurfel over the whole model (loop-closure hook) */
+void orc_engine_transform_model(OrcEngine*, const float* R9, const float* t3);
+/* extractLocalPointCloud with the engine's pose, conf_thresh and the given radius; returns the count */
+int orc_engine_local_cloud(const OrcEngine*, float radius, float* out_pos, float* out_nrm);
 void orc_engine_get_model(const OrcEngine*, OrcSurfels* out /* caller buffers, nb_supersurfels rows */);
 void orc_engine_get_frame(const OrcEngine*, OrcSurfels* out /* caller buffers, S rows */);
 OrcTps* orc_engine_tps(OrcEngine*);
@@ -133,6 +150,16 @@ void orc_apply_deformation(float* positions, float* orientations, float* shapes,
 void orc_markers(const float* positions, const float* colors, const float* orientations, const float* dims,
                  const float* confidences, int n, float conf_thresh, float* points, float* out_colors);
 int orc_format_tum_pose(const float* R9, const float* t3, const char* timestamp, char* line, int line_size);
+/* extractLocalPointCloudKernel (supersurfel_fusion_kernels.cu:490-520) + the view transform of its caller
+ * (supersurfel_fusion.cu:896-897): stable supersurfels (conf >= conf_thresh) within `radius` of the camera,
+ * in camera coordinates, ascending model order (the reference's order is by atomic ticket).  Returns the count. */
+int orc_extract_local_point_cloud(int n, const float* positions, const float* orientations, const float* confidences,
+                                  float conf_thresh, const float* R_pose9, const float* t_pose3, float radius,
+                                  float* out_pos, float* out_nrm);
+/* applyTransformSuperSurfel (supersurfel_fusion_kernels.cu:467-488): rigid motion of every supersurfel with
+ * confidence > 0 (position, orientation rows, shape). */
+void orc_transform_model(int n, float* positions, float* orientations, float* shapes, const float* confidences,
+                         const float* R9, const float* t3);
 
 /* ---- ingest in front of the path (supersurfel_fusion.cu:171-181; oracle_ingest.cpp) */
 void orc_bilateral_filter(const float* depth, int width, int height, int kernel_size, float sigma_color,

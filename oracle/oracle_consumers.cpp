@@ -4,6 +4,8 @@
 //   quatToRotMat/rotMatToQuat  core/include/supersurfel_fusion/matrix_math.cuh:512-585
 //   marker geometry            node/supersurfel_fusion_node.cpp:303-413
 //   TUM trajectory line        node/supersurfel_fusion_rgbd_benchmark_node.cpp:616-620,727-729
+//   extractLocalPointCloud     core/src/supersurfel_fusion_kernels.cu:490-520, supersurfel_fusion.cu:884-920
+//   applyTransformSuperSurfel  core/src/supersurfel_fusion_kernels.cu:467-488
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -99,6 +101,49 @@ void orc_apply_deformation(float* positions, float* orientations, float* shapes,
     const Cov3 S = mult_ABAt(av, mkcov(sh[0], sh[1], sh[2], sh[3], sh[4], sh[5]));
     sh[0] = S.xx; sh[1] = S.xy; sh[2] = S.xz; sh[3] = S.yy; sh[4] = S.yz; sh[5] = S.zz;
     positions[3 * i] = po.x; positions[3 * i + 1] = po.y; positions[3 * i + 2] = po.z;
+  }
+}
+
+// extractLocalPointCloudKernel (supersurfel_fusion_kernels.cu:490-520) with the view transform its caller
+// builds from the pose (supersurfel_fusion.cu:896-897: R_view = R^T, t_view = -R_view t).  The reference
+// appends by atomic ticket; here ascending model order (compare order-insensitively).
+int orc_extract_local_point_cloud(int n, const float* positions, const float* orientations, const float* confidences,
+                                  float conf_thresh, const float* R_pose9, const float* t_pose3, float radius,
+                                  float* out_pos, float* out_nrm) {
+  const Mat33 R = mkmat(mk3(R_pose9[0], R_pose9[1], R_pose9[2]), mk3(R_pose9[3], R_pose9[4], R_pose9[5]),
+                        mk3(R_pose9[6], R_pose9[7], R_pose9[8]));
+  const Mat33 Rv = transpose(R);
+  const f3 tv = -(Rv * mk3(t_pose3[0], t_pose3[1], t_pose3[2]));
+  int count = 0;
+  for (int k = 0; k < n; k++) {
+    if (!(confidences[k] >= conf_thresh)) continue;
+    const f3 p = Rv * mk3(positions[3 * k], positions[3 * k + 1], positions[3 * k + 2]) + tv;
+    if (!(length(p) < radius)) continue;
+    const float* o = orientations + 9 * k;
+    const f3 nrm = normalize(Rv * mk3(o[6], o[7], o[8]));     // rows[2] = normal
+    out_pos[3 * count] = p.x; out_pos[3 * count + 1] = p.y; out_pos[3 * count + 2] = p.z;
+    out_nrm[3 * count] = nrm.x; out_nrm[3 * count + 1] = nrm.y; out_nrm[3 * count + 2] = nrm.z;
+    count++;
+  }
+  return count;
+}
+
+// applyTransformSuperSurfel (supersurfel_fusion_kernels.cu:467-488)
+void orc_transform_model(int n, float* positions, float* orientations, float* shapes, const float* confidences,
+                         const float* R9, const float* t3) {
+  const Mat33 R = mkmat(mk3(R9[0], R9[1], R9[2]), mk3(R9[3], R9[4], R9[5]), mk3(R9[6], R9[7], R9[8]));
+  const f3 t = mk3(t3[0], t3[1], t3[2]);
+  const Mat33 Rt = transpose(R);
+  for (int k = 0; k < n; k++) {
+    if (confidences[k] <= 0.0f) continue;
+    const f3 p = R * mk3(positions[3 * k], positions[3 * k + 1], positions[3 * k + 2]) + t;
+    positions[3 * k] = p.x; positions[3 * k + 1] = p.y; positions[3 * k + 2] = p.z;
+    float* o = orientations + 9 * k;
+    const Mat33 On = mkmat(mk3(o[0], o[1], o[2]), mk3(o[3], o[4], o[5]), mk3(o[6], o[7], o[8])) * Rt;
+    for (int r = 0; r < 3; r++) { o[3 * r] = On.rows[r].x; o[3 * r + 1] = On.rows[r].y; o[3 * r + 2] = On.rows[r].z; }
+    float* sh = shapes + 6 * k;
+    const Cov3 S = mult_ABAt(R, mkcov(sh[0], sh[1], sh[2], sh[3], sh[4], sh[5]));
+    sh[0] = S.xx; sh[1] = S.xy; sh[2] = S.xz; sh[3] = S.yy; sh[4] = S.yz; sh[5] = S.zz;
   }
 }
 

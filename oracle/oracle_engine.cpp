@@ -72,6 +72,11 @@ extern "C" void orc_engine_destroy(OrcEngine* e) {
 
 extern "C" void orc_engine_process_frame(OrcEngine* e, const uint8_t* rgb, const float* depth,
                                          const float* prior, OrcFrameStats* stats) {
+  orc_engine_process_frame_masked(e, rgb, depth, prior, nullptr, stats);
+}
+
+extern "C" void orc_engine_process_frame_masked(OrcEngine* e, const uint8_t* rgb, const float* depth,
+                                                const float* prior, const uint8_t* mask, OrcFrameStats* stats) {
   const OrcConfig& c = e->cfg;
   // tps->compute / filter / computeDepthImage (supersurfel_fusion.cu:189-191)
   orc_tps_compute(e->tps, rgb, depth);
@@ -81,6 +86,10 @@ extern "C" void orc_engine_process_frame(OrcEngine* e, const uint8_t* rgb, const
   OrcSurfels frame = e->frame();
   orc_generate_supersurfels(&c.cam, e->S, e->rgba.data(), e->slanted.data(), e->labels.data(),
                             e->inliers.data(), e->bound.data(), c.range_min, c.range_max, e->stamp, &frame);
+  // MOD hook: detectMotion marks dynamic frame supersurfels invalid (:198-213, motion_detection.cu:573)
+  if (mask)
+    for (int f = 0; f < e->S; f++)
+      if (mask[f]) e->f_cnf[f] = -1.0f;
   // pose prior (:225-228)
   if (prior) {
     for (int i = 0; i < 9; i++) e->R[i] = prior[i];
@@ -123,6 +132,11 @@ extern "C" void orc_engine_process_frame(OrcEngine* e, const uint8_t* rgb, const
     stats->icp_iters = is.iters;
     stats->icp_inliers = is.inliers;
     stats->icp_error = is.error;
+    stats->nb_matched = fc.nb_matched;
+    stats->nb_inserted = fc.nb_inserted;
+    stats->nb_removed_stale = fc.nb_removed_stale;
+    stats->nb_removed_invalid = fc.nb_removed_invalid;
+    stats->nb_removed_occluded = fc.nb_removed_occluded;
   }
   e->stamp++;  // :521
 }
@@ -130,6 +144,17 @@ extern "C" void orc_engine_process_frame(OrcEngine* e, const uint8_t* rgb, const
 extern "C" void orc_engine_get_pose(const OrcEngine* e, float* R9, float* t3) {
   for (int i = 0; i < 9; i++) R9[i] = e->R[i];
   for (int i = 0; i < 3; i++) t3[i] = e->t[i];
+}
+extern "C" void orc_engine_set_pose(OrcEngine* e, const float* R9, const float* t3) {
+  for (int i = 0; i < 9; i++) e->R[i] = R9[i];
+  for (int i = 0; i < 3; i++) e->t[i] = t3[i];
+}
+extern "C" void orc_engine_transform_model(OrcEngine* e, const float* R9, const float* t3) {
+  orc_transform_model(e->nbSupersurfels, e->m_pos.data(), e->m_ori.data(), e->m_shp.data(), e->m_cnf.data(), R9, t3);
+}
+extern "C" int orc_engine_local_cloud(const OrcEngine* e, float radius, float* out_pos, float* out_nrm) {
+  return orc_extract_local_point_cloud(e->nbSupersurfels, e->m_pos.data(), e->m_ori.data(), e->m_cnf.data(),
+                                       e->cfg.conf_thresh, e->R, e->t, radius, out_pos, out_nrm);
 }
 static void copy_out(const OrcSurfels& s, OrcSurfels* o, size_t n) {
   if (o->positions) std::memcpy(o->positions, s.positions, n * 12);

@@ -132,6 +132,7 @@ extern "C" void orc_fuse(const OrcCam* cam, int S, const OrcSurfels* frame_in, O
   int nbSupersurfels = counts->nb_supersurfels;
   int nbVisible = counts->nb_visible;
   int nbRemoved = 0, nbMatched = 0, nbInserted = 0;
+  counts->nb_removed_stale = counts->nb_removed_invalid = counts->nb_removed_occluded = 0;
 
   if (nbSupersurfels > 0) {
     std::vector<unsigned char> matched(S, 0);
@@ -235,6 +236,8 @@ extern "C" void orc_fuse(const OrcCam* cam, int S, const OrcSurfels* frame_in, O
         int time_diff = stamp - model->stamps[2 * i + 1];
         float conf = model->confidences[i];
         if ((time_diff > delta_t && conf < conf_thresh && stamp > delta_t) || conf <= 0.0f) {
+          if (time_diff > delta_t && conf < conf_thresh && stamp > delta_t) counts->nb_removed_stale++;
+          else counts->nb_removed_invalid++;
           model->confidences[i] = -1.0f;
           state = 2;
         } else {
@@ -244,7 +247,7 @@ extern "C" void orc_fuse(const OrcCam* cam, int S, const OrcSurfels* frame_in, O
             float v = cam->fy * p.y / p.z + cam->cy;
             if (u >= 0.0f && u < (float)W && v >= 0.0f && v < (float)H) {
               float z = slanted_depth[tex_coord(v, H) * W + tex_coord(u, W)];
-              if (p.z < 0.8f * z) { model->confidences[i] = -1.0f; state = 2; }
+              if (p.z < 0.8f * z) { model->confidences[i] = -1.0f; state = 2; counts->nb_removed_occluded++; }
             } else state = 1;
           } else state = 1;
         }

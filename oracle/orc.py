@@ -54,13 +54,16 @@ class OrcIcpStats(C.Structure):
 
 class OrcFuseCounts(C.Structure):
     _fields_ = [("nb_supersurfels", C.c_int), ("nb_visible", C.c_int), ("nb_removed", C.c_int),
-                ("nb_matched", C.c_int), ("nb_inserted", C.c_int)]
+                ("nb_matched", C.c_int), ("nb_inserted", C.c_int), ("nb_removed_stale", C.c_int),
+                ("nb_removed_invalid", C.c_int), ("nb_removed_occluded", C.c_int)]
 
 
 class OrcFrameStats(C.Structure):
     _fields_ = [("stamp", C.c_int), ("nb_supersurfels", C.c_int), ("nb_visible", C.c_int),
                 ("nb_removed", C.c_int), ("icp_ran", C.c_int), ("icp_valid", C.c_int),
-                ("icp_iters", C.c_int), ("icp_inliers", C.c_float), ("icp_error", C.c_double)]
+                ("icp_iters", C.c_int), ("icp_inliers", C.c_float), ("icp_error", C.c_double),
+                ("nb_matched", C.c_int), ("nb_inserted", C.c_int), ("nb_removed_stale", C.c_int),
+                ("nb_removed_invalid", C.c_int), ("nb_removed_occluded", C.c_int)]
 
 
 _lib = None
@@ -216,7 +219,27 @@ def fuse(cam, frame, model, nb_max, R, t, labels, slanted, z_min, z_max, stamp, 
                    _p(labels), _p(slanted), C.c_float(z_min), C.c_float(z_max), C.c_int(stamp),
                    C.c_int(delta_t), C.c_float(conf_thresh), C.byref(fc))
     return dict(nb_supersurfels=fc.nb_supersurfels, nb_visible=fc.nb_visible, nb_removed=fc.nb_removed,
-                nb_matched=fc.nb_matched, nb_inserted=fc.nb_inserted)
+                nb_matched=fc.nb_matched, nb_inserted=fc.nb_inserted, nb_removed_stale=fc.nb_removed_stale,
+                nb_removed_invalid=fc.nb_removed_invalid, nb_removed_occluded=fc.nb_removed_occluded)
+
+
+def extract_local_point_cloud(surfels, conf_thresh, R_pose, t_pose, radius):
+    """extractLocalPointCloud (supersurfel_fusion.cu:884-920) -> (positions, normals) in camera coordinates."""
+    n = surfels.n
+    pos = np.zeros((max(n, 1), 3), np.float32)
+    nrm = np.zeros((max(n, 1), 3), np.float32)
+    lib().orc_extract_local_point_cloud.restype = C.c_int
+    cnt = lib().orc_extract_local_point_cloud(C.c_int(n), _p(surfels.positions), _p(surfels.orientations),
+                                              _p(surfels.confidences), C.c_float(conf_thresh),
+                                              _p(_f32(np.asarray(R_pose).reshape(9))), _p(_f32(np.asarray(t_pose).reshape(3))),
+                                              C.c_float(radius), _p(pos), _p(nrm))
+    return pos[:cnt], nrm[:cnt]
+
+
+def transform_model(surfels, R, t):
+    """applyTransformSuperSurfel (supersurfel_fusion_kernels.cu:467-488), in place."""
+    lib().orc_transform_model(C.c_int(surfels.n), _p(surfels.positions), _p(surfels.orientations), _p(surfels.shapes),
+                              _p(surfels.confidences), _p(_f32(np.asarray(R).reshape(9))), _p(_f32(np.asarray(t).reshape(3))))
 
 
 class Tps:
@@ -263,14 +286,16 @@ class Engine:
         self.S = self.tps.S
         self.last = None
 
-    def process_frame(self, rgb, depth, prior=None):
+    def process_frame(self, rgb, depth, prior=None, mask=None):
+        """mask: optional uint8[S], the MOD hook (dynamic frame supersurfels -> confidence -1)."""
         rgb = np.ascontiguousarray(rgb, np.uint8)
         depth = _f32(depth)
         pr = None
         if prior is not None:
             pr = _f32(np.concatenate([np.asarray(prior[0]).reshape(9), np.asarray(prior[1]).reshape(3)]))
+        mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         st = OrcFrameStats()
-        lib().orc_engine_process_frame(self.h, _p(rgb), _p(depth), _p(pr), C.byref(st))
+        lib().orc_engine_process_frame_masked(self.h, _p(rgb), _p(depth), _p(pr), _p(mk), C.byref(st))
         self.last = {k: getattr(st, k) for k, _ in OrcFrameStats._fields_}
         return self.last
 
@@ -279,6 +304,20 @@ class Engine:
         t = np.zeros(3, np.float32)
         lib().orc_engine_get_pose(self.h, _p(R), _p(t))
         return R.reshape(3, 3), t
+
+    def set_pose(self, R, t):
+        lib().orc_engine_set_pose(self.h, _p(_f32(np.asarray(R).reshape(9))), _p(_f32(np.asarray(t).reshape(3))))
+
+    def transform_model(self, R, t):
+        lib().orc_engine_transform_model(self.h, _p(_f32(np.asarray(R).reshape(9))), _p(_f32(np.asarray(t).reshape(3))))
+
+    def local_cloud(self, radius):
+        n = max(self.last["nb_supersurfels"] if self.last else 0, 1)
+        pos = np.zeros((n, 3), np.float32)
+        nrm = np.zeros((n, 3), np.float32)
+        lib().orc_engine_local_cloud.restype = C.c_int
+        cnt = lib().orc_engine_local_cloud(self.h, C.c_float(radius), _p(pos), _p(nrm))
+        return pos[:cnt], nrm[:cnt]
 
     def model(self):
         n = self.last["nb_supersurfels"] if self.last else 0

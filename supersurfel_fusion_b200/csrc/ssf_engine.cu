@@ -14,6 +14,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace ssf {
 
 void launch_icp_set_transform(Engine* e, const float* R, const float* t);
@@ -70,12 +72,13 @@ struct EngineImpl : public SsfEngine {
   int pipe_next;     // slot of the next submitted frame
   int pipe_oldest;   // slot of the oldest frame in flight
   int in_flight;
-  uint64_t launches_per_frame[2];
+  uint64_t launches_per_frame[4];
+  cudaEvent_t ev_tm[6];            // stage boundaries of a frame run with SSF_FLAG_STAGE_TIMING
   FrameReport* d_report;
   FrameReport* h_report;
   float* h_prior;          // pinned 12 floats
-  cudaGraphExec_t graph_exec[2];   // [0] depth used as given, [1] SSF_FLAG_BILATERAL
-  bool graph_ready[2];
+  cudaGraphExec_t graph_exec[4];   // bit 0: SSF_FLAG_BILATERAL, bit 1: SSF_FLAG_STAGE_TIMING (event nodes at stage boundaries)
+  bool graph_ready[4];
   bool use_graph;
   bool created;
 };
@@ -104,30 +107,50 @@ static void select_slot(EngineImpl* e, int s) {
 
 // The frame as a sequence of steps: 0 = ingest, 1 .. T = the segmentation steps (tps_step_count),
 // T + 1 = extraction, T + 2 = registration + fusion.  enqueue_steps enqueues [g0, g1).
-static int frame_step_count(const EngineImpl* e) { return tps_step_count(e) + 3; }
+static void enqueue_track(EngineImpl* e, FrameReport* report, int advance, bool marks);
 
-static void enqueue_track(EngineImpl* e, FrameReport* report, int advance);
+// NVTX range on the host side of the enqueue (SSF_NVTX=1): shows the stage structure of a frame
+// in a timeline next to the kernels; under graph replay only the capture carries the ranges.
+struct StageRange {
+  bool on;
+  StageRange(const EngineImpl* e, const char* name) : on(e->nvtx != 0) { if (on) nvtxRangePushA(name); }
+  ~StageRange() { if (on) nvtxRangePop(); }
+};
+// stage boundary k of a frame run with SSF_FLAG_STAGE_TIMING (an event-record node under capture)
+static void stage_mark(EngineImpl* e, bool marks, int k) {
+  if (marks) cudaEventRecord(e->ev_tm[k], e->stream);
+}
 
-static void enqueue_steps(EngineImpl* e, int g0, int g1, bool bilateral, bool pipelined, FrameReport* report) {
+static void enqueue_steps(EngineImpl* e, int g0, int g1, bool bilateral, bool pipelined, FrameReport* report,
+                          bool marks = false) {
   const int T = tps_step_count(e);
+  if (g0 <= 0) stage_mark(e, marks, 0);
   if (g0 <= 0 && g1 > 0) {
+    StageRange r(e, "ssf:ingest");
     const float* depth = e->in_depth;
     if (bilateral) {
       launch_bilateral(e, e->in_depth, e->depth_f, kBilateralKernel, kBilateralSigmaColor, kBilateralSigmaSpatial);
       depth = e->depth_f;
     }
     launch_ingest(e, e->in_rgb, (size_t)e->W * 3, depth, (size_t)e->W * 4);
+    stage_mark(e, marks, 1);
   }
   const int t0 = (g0 > 1 ? g0 : 1) - 1, t1 = (g1 < T + 1 ? g1 : T + 1) - 1;
-  if (t1 > t0) launch_tps(e, t0, t1);
+  if (t1 > t0) {
+    StageRange r(e, "ssf:segmentation");
+    launch_tps(e, t0, t1);
+    if (t1 == T) stage_mark(e, marks, 2);
+  }
   if (g0 <= T + 1 && g1 > T + 1) {
+    StageRange r(e, "ssf:extraction");
     launch_extract(e);
+    stage_mark(e, marks, 3);
     if (pipelined) {     // the next frame to be extracted carries the next stamp
       launch_pdl(e, seg_end_kernel, dim3(1), dim3(1), 0, e->counters);
       e->launches++;
     }
   }
-  if (g0 <= T + 2 && g1 > T + 2) enqueue_track(e, report, pipelined ? 1 : 3);
+  if (g0 <= T + 2 && g1 > T + 2) enqueue_track(e, report, pipelined ? 1 : 3, marks);
 }
 
 // Cut the frame's steps (0 = ingest, 1 .. T = segmentation steps, T + 1 = extraction, T + 2 =
@@ -175,23 +198,29 @@ static void plan_stages(EngineImpl* e, int stages) {
   e->nb_stages = plan_stages_impl(e->cfg.seg_iter, e->cfg.icp_iter, e->tps_persistent, stages, e->stage_first);
 }
 
-static void enqueue_seg(EngineImpl* e, bool bilateral) {
-  enqueue_steps(e, 0, tps_step_count(e) + 2, bilateral, false, nullptr);
+static void enqueue_seg(EngineImpl* e, bool bilateral, bool marks) {
+  enqueue_steps(e, 0, tps_step_count(e) + 2, bilateral, false, nullptr, marks);
 }
 
 // stage C: registration + fusion (reads the slot's hand-over set, owns pose / model / counters)
-static void enqueue_track(EngineImpl* e, FrameReport* report, int advance) {
-  launch_icp_begin_from_pose(e);
-  launch_icp_loop(e);
-  launch_icp_finish(e, true);
+static void enqueue_track(EngineImpl* e, FrameReport* report, int advance, bool marks) {
+  {
+    StageRange r(e, "ssf:registration");
+    launch_icp_begin_from_pose(e);
+    launch_icp_loop(e);
+    launch_icp_finish(e, true);
+    stage_mark(e, marks, 4);
+  }
+  StageRange r(e, "ssf:fusion");
   launch_fuse(e);
   launch_pdl(e, frame_end_kernel, dim3(1), dim3(1), 0, e->counters, e->pose, e->icp, report, advance);
   e->launches++;
+  stage_mark(e, marks, 5);
 }
 
-static void enqueue_frame(EngineImpl* e, bool bilateral) {
-  enqueue_seg(e, bilateral);
-  enqueue_track(e, e->d_report, 3);
+static void enqueue_frame(EngineImpl* e, bool bilateral, bool marks) {
+  enqueue_seg(e, bilateral, marks);
+  enqueue_track(e, e->d_report, 3, marks);
 }
 
 static int ensure_scratch(EngineImpl* e, size_t bytes) {
@@ -253,6 +282,19 @@ static void fill_stats(EngineImpl* e, float gpu_ms) {
   s.icp_inliers = r.icp_inliers;
   s.icp_error = r.icp_error;
   s.gpu_ms = gpu_ms;
+  s.ms_ingest = s.ms_segmentation = s.ms_extraction = s.ms_registration = s.ms_fusion = 0.f;
+}
+
+// per-stage device times of the frame just run with SSF_FLAG_STAGE_TIMING (what the reference prints
+// per frame, supersurfel_fusion.cu:516-528)
+static void fill_stage_ms(EngineImpl* e) {
+  float* dst[5] = {&e->stats.ms_ingest, &e->stats.ms_segmentation, &e->stats.ms_extraction, &e->stats.ms_registration,
+                   &e->stats.ms_fusion};
+  for (int k = 0; k < 5; k++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev_tm[k], e->ev_tm[k + 1]) != cudaSuccess) { ms = 0.f; cudaGetLastError(); }
+    *dst[k] = ms;
+  }
 }
 
 }  // namespace ssf
@@ -262,7 +304,35 @@ using namespace ssf;
 #define H_CHECK(h)                                  \
   if (!(h)) return SSF_ERR_INVALID_ARG;             \
   EngineImpl* e = static_cast<EngineImpl*>(h);      \
+  if (e->failed) return SSF_ERR_STATE;              \
   cudaSetDevice(e->device)
+
+// Every entry point that touches device state outside the pipeline (everything except
+// ssf_submit_frame / ssf_wait_frame / the pure getters) refuses while frames are in flight:
+// the last-stage stream owns pose, model, counters and the registration state then.
+#define H_CHECK_IDLE(h)                                                          \
+  H_CHECK(h);                                                                    \
+  if (e->in_flight) {                                                            \
+    e->err = "pipelined frames in flight: ssf_wait_frame first";                 \
+    return SSF_ERR_STATE;                                                        \
+  }
+
+// first kernel-launch failure since the last check (launch_pdl records it), then the sticky error
+static int launch_status(EngineImpl* e) {
+  cudaError_t rc = e->launch_err;
+  e->launch_err = cudaSuccess;
+  if (rc == cudaSuccess) rc = cudaGetLastError();
+  if (rc != cudaSuccess) {
+    e->err = std::string("kernel launch: ") + cudaGetErrorString(rc);
+    return SSF_ERR_CUDA;
+  }
+  return SSF_OK;
+}
+#define SSF_LAUNCH_OK(e)                 \
+  do {                                   \
+    const int _rc = launch_status(e);    \
+    if (_rc) return _rc;                 \
+  } while (0)
 
 extern "C" {
 
@@ -279,7 +349,7 @@ int ssf_config_default(SsfConfig* c) {
   c->range_min = 0.2f; c->range_max = 5.0f;
   c->delta_t = 20; c->conf_thresh = 2500.0f; c->nb_supersurfels_max = 50000;
   c->icp_iter = 10; c->icp_cov_thresh = 0.04;
-  c->enable_loop_closure = 0; c->enable_mod = 0;
+  c->enable_loop_closure = 1; c->enable_mod = 1;   /* supersurfel_fusion.hpp:72-73; recorded, see ssf.h */
   return SSF_OK;
 }
 
@@ -287,8 +357,7 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   if (!cfg || !out) return SSF_ERR_INVALID_ARG;
   *out = nullptr;
   if (cfg->cam.width <= 0 || cfg->cam.height <= 0 || cfg->cell_size < 2 || cfg->nb_supersurfels_max <= 0 ||
-      cfg->nb_samples <= 0 || cfg->nb_samples > 1024 || cfg->seg_iter < 0 || cfg->icp_iter < 1 ||
-      cfg->enable_loop_closure || cfg->enable_mod)
+      cfg->nb_samples <= 0 || cfg->nb_samples > 1024 || cfg->seg_iter < 0 || cfg->icp_iter < 1)
     return SSF_ERR_INVALID_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return SSF_ERR_NO_DEVICE;
@@ -298,7 +367,11 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   e->cfg = *cfg;
   e->device = device;
   e->launches = 0;
-  e->graph_ready[0] = e->graph_ready[1] = false;
+  e->launch_err = cudaSuccess;
+  e->failed = 0;
+  e->nvtx = 0;
+  if (const char* v = getenv("SSF_NVTX")) e->nvtx = atoi(v) != 0;
+  for (int k = 0; k < 4; k++) e->graph_ready[k] = false;
   e->use_graph = true;
   e->created = false;
   e->W = cfg->cam.width; e->H = cfg->cam.height;
@@ -337,6 +410,7 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   A(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   e->stream = e->own_stream;
   A(cudaEventCreate(&e->ev0)); A(cudaEventCreate(&e->ev1)); A(cudaEventCreate(&e->evf0)); A(cudaEventCreate(&e->evf1));
+  for (int k = 0; k < 6; k++) A(cudaEventCreate(&e->ev_tm[k]));
   const size_t N = e->npix;
   const int S = e->S, nbs = cfg->nb_samples;
   A(dalloc(&e->rgba, N)); A(dalloc(&e->disp, N)); A(dalloc(&e->labels, N)); A(dalloc(&e->bound, N));
@@ -429,8 +503,10 @@ int ssf_destroy(SsfHandle h) {
   EngineImpl* e = static_cast<EngineImpl*>(h);
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
-  for (int k = 0; k < 2; k++)
+  for (int k = 0; k < 4; k++)
     if (e->graph_ready[k]) cudaGraphExecDestroy(e->graph_exec[k]);
+  for (int k = 0; k < 6; k++)
+    if (e->ev_tm[k]) cudaEventDestroy(e->ev_tm[k]);
   if (e->slot[0].lmap) select_slot(e, 0);
   for (int k = 0; k < SSF_SLOTS; k++) {
     for (int p = 0; p < SSF_SLOTS; p++) {
@@ -474,11 +550,11 @@ int ssf_destroy(SsfHandle h) {
 }
 
 int ssf_set_stream(SsfHandle h, void* cuda_stream) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (e->in_flight) { e->err = "pipelined frames in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
-  for (int k = 0; k < 2; k++)
+  for (int k = 0; k < 4; k++)
     if (e->graph_ready[k]) { cudaGraphExecDestroy(e->graph_exec[k]); e->graph_ready[k] = false; }
   for (int k = 0; k < SSF_SLOTS; k++)
     for (int p = 0; p < SSF_SLOTS; p++)
@@ -495,7 +571,8 @@ const char* ssf_last_error(SsfHandle h) {
 int ssf_is_initialized(SsfHandle h) { return (h && static_cast<EngineImpl*>(h)->created) ? 1 : 0; }
 
 static int run_frame(EngineImpl* e, const float* prior, uint32_t flags) {
-  const int gi = (flags & SSF_FLAG_BILATERAL) ? 1 : 0;
+  const bool marks = (flags & SSF_FLAG_STAGE_TIMING) != 0;
+  const int gi = ((flags & SSF_FLAG_BILATERAL) ? 1 : 0) | (marks ? 2 : 0);
   if (e->in_flight) { e->err = "synchronous frame while pipelined frames are in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
   if (e->cur_slot != 0) select_slot(e, 0);
   if (prior) {
@@ -508,7 +585,7 @@ static int run_frame(EngineImpl* e, const float* prior, uint32_t flags) {
       cudaGraph_t g;
       const uint64_t before = e->launches;
       SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-      enqueue_frame(e, gi != 0);
+      enqueue_frame(e, (gi & 1) != 0, marks);
       SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
       e->launches_per_frame[gi] = e->launches - before;
       e->launches = before;
@@ -519,21 +596,22 @@ static int run_frame(EngineImpl* e, const float* prior, uint32_t flags) {
     SSF_CUDA(e, cudaGraphLaunch(e->graph_exec[gi], e->stream));
     e->launches += e->launches_per_frame[gi];
   } else {
-    enqueue_frame(e, gi != 0);
+    enqueue_frame(e, (gi & 1) != 0, marks);
   }
   SSF_CUDA(e, cudaEventRecord(e->evf1, e->stream));
   SSF_CUDA(e, cudaMemcpyAsync(e->h_report, e->d_report, sizeof(FrameReport), cudaMemcpyDeviceToHost, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e->evf0, e->evf1);
   fill_stats(e, ms);
+  if (marks) fill_stage_ms(e);
   return SSF_OK;
 }
 
 int ssf_process_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth, size_t depth_stride,
                       const float* pose_prior_Rt12, uint32_t flags) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!rgb || !depth) return SSF_ERR_INVALID_ARG;
   if (rgb_stride == 0) rgb_stride = (size_t)e->W * 3;
   if (depth_stride == 0) depth_stride = (size_t)e->W * 4;
@@ -546,7 +624,7 @@ int ssf_process_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const 
 
 int ssf_process_frame_device(SsfHandle h, const uint8_t* rgb_dev, const float* depth_dev, const float* pose_prior_Rt12,
                              uint32_t flags) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!rgb_dev || !depth_dev) return SSF_ERR_INVALID_ARG;
   SSF_CUDA(e, cudaMemcpyAsync(e->in_rgb, rgb_dev, e->npix * 3, cudaMemcpyDeviceToDevice, e->stream));
   SSF_CUDA(e, cudaMemcpyAsync(e->in_depth, depth_dev, e->npix * 4, cudaMemcpyDeviceToDevice, e->stream));
@@ -555,7 +633,7 @@ int ssf_process_frame_device(SsfHandle h, const uint8_t* rgb_dev, const float* d
 
 int ssf_process_frame_depth16(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const uint16_t* depth16,
                               size_t depth_stride, float depth_scale, const float* pose_prior_Rt12, uint32_t flags) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!rgb || !depth16) return SSF_ERR_INVALID_ARG;
   if (rgb_stride == 0) rgb_stride = (size_t)e->W * 3;
   if (depth_stride == 0) depth_stride = (size_t)e->W * 2;
@@ -569,32 +647,33 @@ int ssf_process_frame_depth16(SsfHandle h, const uint8_t* rgb, size_t rgb_stride
 
 int ssf_bilateral_filter(SsfHandle h, const float* depth, size_t depth_stride, int kernel_size, float sigma_color,
                          float sigma_spatial, float* out) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!depth || !out) return SSF_ERR_INVALID_ARG;
   if (depth_stride == 0) depth_stride = (size_t)e->W * 4;
+  if (depth_stride < (size_t)e->W * 4) return SSF_ERR_INVALID_ARG;
   SSF_CUDA(e, cudaMemcpy2DAsync(e->in_depth, (size_t)e->W * 4, depth, depth_stride, (size_t)e->W * 4, e->H, cudaMemcpyDefault, e->stream));
   int rc = launch_bilateral(e, e->in_depth, e->depth_f, kernel_size, sigma_color, sigma_spatial);
   if (rc) { e->err = "ssf_bilateral_filter: kernel radius above the supported 12"; return rc; }
   SSF_CUDA(e, cudaMemcpyAsync(out, e->depth_f, e->npix * 4, cudaMemcpyDefault, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_get_gray(SsfHandle h, uint8_t* gray) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!gray) return SSF_ERR_INVALID_ARG;
   int rc = ensure_scratch(e, e->npix);
   if (rc) return rc;
   launch_gray(e, e->in_rgb, reinterpret_cast<uint8_t*>(e->scratch));
   SSF_CUDA(e, cudaMemcpyAsync(gray, e->scratch, e->npix, cudaMemcpyDefault, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_get_filtered_depth(SsfHandle h, float* depth) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!depth) return SSF_ERR_INVALID_ARG;
   SSF_CUDA(e, cudaMemcpyAsync(depth, e->depth_f, e->npix * 4, cudaMemcpyDefault, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -624,25 +703,10 @@ static int capture_stage(EngineImpl* e, int slot, int stage, int gi) {
   return SSF_OK;
 }
 
-int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth, size_t depth_stride,
-                     const float* pose_prior_Rt12, uint32_t flags) {
-  H_CHECK(h);
-  if (!rgb || !depth) return SSF_ERR_INVALID_ARG;
-  if (rgb_stride == 0) rgb_stride = (size_t)e->W * 3;
-  if (depth_stride == 0) depth_stride = (size_t)e->W * 4;
-  if (rgb_stride < (size_t)e->W * 3 || depth_stride < (size_t)e->W * 4) return SSF_ERR_INVALID_ARG;
+// Everything of ssf_submit_frame that can fail after work was enqueued; see the caller.
+static int submit_enqueue(EngineImpl* e, int s, const uint8_t* rgb, size_t rgb_stride, const float* depth,
+                          size_t depth_stride, const float* pose_prior_Rt12, uint32_t flags) {
   const int P = e->nb_stages;
-  if (e->in_flight >= P) { e->err = "every pipeline stage is occupied: ssf_wait_frame first"; return SSF_ERR_STATE; }
-  const int s = e->pipe_next;
-  select_slot(e, s);
-  for (int p = 0; p < P; p++) {
-    const int gi = (p == 0 && (flags & SSF_FLAG_BILATERAL)) ? 1 : 0;   // the ingest is always in stage 0
-    if (!e->stage_ready[s][p][gi]) {
-      int rc = capture_stage(e, s, p, gi);
-      if (rc) return rc;
-    }
-  }
-  if (e->in_flight == 0) e->pipe_oldest = s;
   for (int p = 0; p < P; p++) {
     cudaStream_t st = p == 0 ? e->stream : e->stage_stream[p];
     const int gi = (p == 0 && (flags & SSF_FLAG_BILATERAL)) ? 1 : 0;
@@ -669,6 +733,89 @@ int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const f
       SSF_CUDA(e, cudaEventRecord(e->ev_done[s], st));
     }
   }
+  return SSF_OK;
+}
+
+// capture + instantiate + upload whatever graphs of the pipelined mode are still missing
+static int prepare_pipeline(EngineImpl* e, uint32_t flags) {
+  const int P = e->nb_stages;
+  const int keep = e->cur_slot;
+  for (int s = 0; s < P; s++) {
+    select_slot(e, s);
+    for (int p = 0; p < P; p++) {
+      const int gi = (p == 0 && (flags & SSF_FLAG_BILATERAL)) ? 1 : 0;   // the ingest is always in stage 0
+      if (e->stage_ready[s][p][gi]) continue;
+      int rc = capture_stage(e, s, p, gi);
+      if (rc) { select_slot(e, keep); return rc; }
+      SSF_CUDA(e, cudaGraphUpload(e->stage_graph[s][p][gi], p == 0 ? e->stream : e->stage_stream[p]));
+    }
+  }
+  select_slot(e, keep);
+  return SSF_OK;
+}
+
+int ssf_prepare(SsfHandle h, uint32_t flags) {
+  H_CHECK_IDLE(h);
+  int rc = prepare_pipeline(e, flags);
+  if (rc) return rc;
+  // the synchronous frame graph too
+  const bool marks = (flags & SSF_FLAG_STAGE_TIMING) != 0;
+  const int gi = ((flags & SSF_FLAG_BILATERAL) ? 1 : 0) | (marks ? 2 : 0);
+  if (e->use_graph && !e->graph_ready[gi]) {
+    if (e->cur_slot != 0) select_slot(e, 0);
+    cudaGraph_t g;
+    const uint64_t before = e->launches;
+    SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    enqueue_frame(e, (gi & 1) != 0, marks);
+    SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
+    e->launches_per_frame[gi] = e->launches - before;
+    e->launches = before;
+    SSF_CUDA(e, cudaGraphInstantiate(&e->graph_exec[gi], g, 0));
+    cudaGraphDestroy(g);
+    e->graph_ready[gi] = true;
+    SSF_CUDA(e, cudaGraphUpload(e->graph_exec[gi], e->stream));
+  }
+  for (int p = 1; p < e->nb_stages; p++) SSF_CUDA(e, cudaStreamSynchronize(e->stage_stream[p]));
+  SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_LAUNCH_OK(e);
+  return SSF_OK;
+}
+
+int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth, size_t depth_stride,
+                     const float* pose_prior_Rt12, uint32_t flags) {
+  H_CHECK(h);
+  if (!rgb || !depth) return SSF_ERR_INVALID_ARG;
+  if (rgb_stride == 0) rgb_stride = (size_t)e->W * 3;
+  if (depth_stride == 0) depth_stride = (size_t)e->W * 4;
+  if (rgb_stride < (size_t)e->W * 3 || depth_stride < (size_t)e->W * 4) return SSF_ERR_INVALID_ARG;
+  const int P = e->nb_stages;
+  if (e->in_flight >= P) { e->err = "every pipeline stage is occupied: ssf_wait_frame first"; return SSF_ERR_STATE; }
+  const int s = e->pipe_next;
+  // graphs first (nothing enqueued yet: a failure here leaves the pipeline as it was)
+  {
+    const int keep = e->cur_slot;
+    select_slot(e, s);
+    for (int p = 0; p < P; p++) {
+      const int gi = (p == 0 && (flags & SSF_FLAG_BILATERAL)) ? 1 : 0;
+      if (!e->stage_ready[s][p][gi]) {
+        int rc = capture_stage(e, s, p, gi);
+        if (rc) { select_slot(e, keep); return rc; }
+      }
+    }
+  }
+  if (e->in_flight == 0) e->pipe_oldest = s;
+  const int rc = submit_enqueue(e, s, rgb, rgb_stride, depth, depth_stride, pose_prior_Rt12, flags);
+  if (rc) {
+    // Part of the frame may be running and its completion event was never recorded: the slot, the
+    // shared staging buffers and the prior buffer cannot be reused safely.  Drain everything and
+    // retire the handle -- every later call returns SSF_ERR_STATE (ssf_last_error keeps the cause).
+    for (int p = 1; p < P; p++) cudaStreamSynchronize(e->stage_stream[p]);
+    cudaStreamSynchronize(e->stream);
+    cudaGetLastError();
+    e->failed = 1;
+    e->err = "ssf_submit_frame failed half-way, handle retired: " + e->err;
+    return rc;
+  }
   e->in_flight++;
   e->pipe_next = (s + 1) % P;
   return SSF_OK;
@@ -679,7 +826,7 @@ int ssf_wait_frame(SsfHandle h, SsfFrameStats* out, float R[9], float t[3]) {
   if (e->in_flight <= 0) { e->err = "no frame in flight"; return SSF_ERR_STATE; }
   const int s = e->pipe_oldest;
   SSF_CUDA(e, cudaEventSynchronize(e->ev_done[s]));
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e->ev_t0[s], e->ev_t1[s]);
   *e->h_report = *e->h_report2[s];
@@ -720,7 +867,8 @@ int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out) {
 }
 
 int ssf_get_pose(SsfHandle h, float R[9], float t[3]) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
+  if (!R || !t) return SSF_ERR_INVALID_ARG;
   int rc = read_report(e, false);
   if (rc) return rc;
   memcpy(R, e->h_report->pose.R, 36);
@@ -729,7 +877,8 @@ int ssf_get_pose(SsfHandle h, float R[9], float t[3]) {
 }
 
 int ssf_set_pose(SsfHandle h, const float R[9], const float t[3]) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
+  if (!R || !t) return SSF_ERR_INVALID_ARG;
   memcpy(e->h_prior, R, 36);
   memcpy(e->h_prior + 9, t, 12);
   SSF_CUDA(e, cudaMemcpyAsync(e->pose, e->h_prior, 48, cudaMemcpyHostToDevice, e->stream));
@@ -738,7 +887,8 @@ int ssf_set_pose(SsfHandle h, const float R[9], const float t[3]) {
 }
 
 int ssf_get_stamp(SsfHandle h, int* stamp) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
+  if (!stamp) return SSF_ERR_INVALID_ARG;
   int rc = read_report(e, false);
   if (rc) return rc;
   *stamp = e->h_report->counters.stamp;
@@ -746,7 +896,7 @@ int ssf_get_stamp(SsfHandle h, int* stamp) {
 }
 
 int ssf_set_stamp(SsfHandle h, int stamp) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   SSF_CUDA(e, cudaMemcpyAsync(&e->counters->stamp, &stamp, sizeof(int), cudaMemcpyHostToDevice, e->stream));
   SSF_CUDA(e, cudaMemcpyAsync(&e->counters->seg_stamp, &stamp, sizeof(int), cudaMemcpyHostToDevice, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -754,7 +904,7 @@ int ssf_set_stamp(SsfHandle h, int stamp) {
 }
 
 int ssf_get_counts(SsfHandle h, int* nb_supersurfels, int* nb_visible, int* nb_removed) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   int rc = read_report(e, false);
   if (rc) return rc;
   if (nb_supersurfels) *nb_supersurfels = e->h_report->counters.nb_supersurfels;
@@ -765,6 +915,7 @@ int ssf_get_counts(SsfHandle h, int* nb_supersurfels, int* nb_visible, int* nb_r
 
 int ssf_get_nb_superpixels(SsfHandle h, int* n) {
   H_CHECK(h);
+  if (!n) return SSF_ERR_INVALID_ARG;
   *n = e->S;
   return SSF_OK;
 }
@@ -804,19 +955,19 @@ static int copy_set_in(EngineImpl* e, const SsfSurfels* src, int n, const Surfel
 }
 
 int ssf_copy_model(SsfHandle h, const SsfSurfels* dst, int n) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (n > e->cap) return SSF_ERR_INVALID_ARG;
   return copy_set_out(e, e->model, dst, n);
 }
 
 int ssf_copy_frame(SsfHandle h, const SsfSurfels* dst) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   return copy_set_out(e, e->frame, dst, e->S);
 }
 
 int ssf_get_segmentation(SsfHandle h, int32_t* labels, int32_t* bound, uint8_t* inliers, float* disp,
                          float* slanted_depth, float* superpixels, uint8_t* rgba) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   const size_t N = e->npix;
   if (labels) SSF_CUDA(e, cudaMemcpyAsync(labels, e->labels, N * 4, cudaMemcpyDefault, e->stream));
   if (bound) SSF_CUDA(e, cudaMemcpyAsync(bound, e->bound, N * 4, cudaMemcpyDefault, e->stream));
@@ -832,6 +983,7 @@ int ssf_get_segmentation(SsfHandle h, int32_t* labels, int32_t* bound, uint8_t* 
     SSF_CUDA(e, cudaMemcpyAsync(slanted_depth, e->scratch, N * 4, cudaMemcpyDefault, e->stream));
   }
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
@@ -840,7 +992,7 @@ int ssf_get_slanted_depth(SsfHandle h, float* depth) {
 }
 
 int ssf_render_preview(SsfHandle h, uint8_t* bgr) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!bgr) return SSF_ERR_INVALID_ARG;
   int rc = ensure_scratch(e, e->npix * 3);
   if (rc) return rc;
@@ -851,7 +1003,7 @@ int ssf_render_preview(SsfHandle h, uint8_t* bgr) {
 }
 
 int ssf_get_model_view(SsfHandle h, SsfPlanarView* out) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!out) return SSF_ERR_INVALID_ARG;
   int rc = read_report(e, false);
   if (rc) return rc;
@@ -863,7 +1015,7 @@ int ssf_get_model_view(SsfHandle h, SsfPlanarView* out) {
 }
 
 int ssf_get_frame_view(SsfHandle h, SsfPlanarView* out) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!out) return SSF_ERR_INVALID_ARG;
   if (e->in_flight) { e->err = "pipelined frames in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
   out->base = e->frame.base;
@@ -874,7 +1026,7 @@ int ssf_get_frame_view(SsfHandle h, SsfPlanarView* out) {
 }
 
 int ssf_export_model(SsfHandle h, const char* path) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!path) return SSF_ERR_INVALID_ARG;
   int rc = read_report(e, false);
   if (rc) return rc;
@@ -906,7 +1058,7 @@ int ssf_export_model(SsfHandle h, const char* path) {
 
 int ssf_extract_local_point_cloud(SsfHandle h, float radius, float* positions, float* normals, int capacity,
                                   int* count) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!positions || !normals || capacity < 0 || !count) return SSF_ERR_INVALID_ARG;
   int rc = ensure_scratch(e, (size_t)capacity * 24 + 16);
   if (rc) return rc;
@@ -928,25 +1080,28 @@ int ssf_extract_local_point_cloud(SsfHandle h, float radius, float* positions, f
 }
 
 int ssf_invalidate_frame_supersurfels(SsfHandle h, const uint8_t* mask) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!mask) return SSF_ERR_INVALID_ARG;
   int rc = ensure_scratch(e, (size_t)e->S);
   if (rc) return rc;
   SSF_CUDA(e, cudaMemcpyAsync(e->scratch, mask, (size_t)e->S, cudaMemcpyDefault, e->stream));
   launch_invalidate(e, reinterpret_cast<const uint8_t*>(e->scratch));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_transform_model(SsfHandle h, const float R[9], const float t[3]) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
+  if (!R || !t) return SSF_ERR_INVALID_ARG;
   launch_transform_model(e, R, t);
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_set_model(SsfHandle h, const SsfSurfels* src, int nb_supersurfels, int nb_visible) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (nb_supersurfels < 0 || nb_supersurfels > e->cap || nb_visible < 0 || nb_visible > nb_supersurfels)
     return SSF_ERR_INVALID_ARG;
   int rc = copy_set_in(e, src, nb_supersurfels, e->model);
@@ -955,21 +1110,23 @@ int ssf_set_model(SsfHandle h, const SsfSurfels* src, int nb_supersurfels, int n
   int c[2] = {nb_supersurfels, nb_visible};
   SSF_CUDA(e, cudaMemcpyAsync(&e->counters->nb_supersurfels, c, 2 * sizeof(int), cudaMemcpyHostToDevice, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_set_frame(SsfHandle h, const SsfSurfels* src) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   int rc = copy_set_in(e, src, e->S, e->frame);
   if (rc) return rc;
   launch_frame_tables(e);
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_set_segmentation(SsfHandle h, const int32_t* labels, const int32_t* bound, const uint8_t* inliers,
                          const float* slanted_depth, const uint8_t* rgba) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   const size_t N = e->npix;
   if (labels) SSF_CUDA(e, cudaMemcpyAsync(e->labels, labels, N * 4, cudaMemcpyDefault, e->stream));
   if (bound) SSF_CUDA(e, cudaMemcpyAsync(e->bound, bound, N * 4, cudaMemcpyDefault, e->stream));
@@ -982,20 +1139,22 @@ int ssf_set_segmentation(SsfHandle h, const int32_t* labels, const int32_t* boun
     launch_build_lmap(e, reinterpret_cast<const float*>(e->scratch));
   }
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_tps_segment(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const float* depth, size_t depth_stride) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!rgb || !depth) return SSF_ERR_INVALID_ARG;
   if (rgb_stride == 0) rgb_stride = (size_t)e->W * 3;
   if (depth_stride == 0) depth_stride = (size_t)e->W * 4;
+  if (rgb_stride < (size_t)e->W * 3 || depth_stride < (size_t)e->W * 4) return SSF_ERR_INVALID_ARG;
   SSF_CUDA(e, cudaMemcpy2DAsync(e->in_rgb, (size_t)e->W * 3, rgb, rgb_stride, (size_t)e->W * 3, e->H, cudaMemcpyDefault, e->stream));
   SSF_CUDA(e, cudaMemcpy2DAsync(e->in_depth, (size_t)e->W * 4, depth, depth_stride, (size_t)e->W * 4, e->H, cudaMemcpyDefault, e->stream));
   launch_ingest(e, e->in_rgb, (size_t)e->W * 3, e->in_depth, (size_t)e->W * 4);
   launch_tps(e);
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   if (e->tps_trace) {   // profiling aid: dump the per-CTA phase timestamps of this call
     std::vector<unsigned long long> host(tps_trace_bytes(e->tps_grid) / 8);
     cudaMemcpy(host.data(), e->tps_trace, host.size() * 8, cudaMemcpyDeviceToHost);
@@ -1006,17 +1165,18 @@ int ssf_tps_segment(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const fl
 }
 
 int ssf_get_ransac_samples(SsfHandle h, float* samples) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
+  if (!samples) return SSF_ERR_INVALID_ARG;
   SSF_CUDA(e, cudaMemcpyAsync(samples, e->samples, (size_t)e->S * e->cfg.nb_samples * sizeof(float4), cudaMemcpyDefault, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   return SSF_OK;
 }
 
 int ssf_generate_supersurfels(SsfHandle h) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   launch_extract(e);
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
@@ -1032,7 +1192,7 @@ static int resolve_n(EngineImpl* e, int n_src, int* out) {
 }
 
 int ssf_icp_system(SsfHandle h, const float R[9], const float t[3], int n_src, float out29[29]) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!R || !t || !out29) return SSF_ERR_INVALID_ARG;
   int n = 0;
   int rc = resolve_n(e, n_src, &n);
@@ -1042,12 +1202,12 @@ int ssf_icp_system(SsfHandle h, const float R[9], const float t[3], int n_src, f
   else SSF_CUDA(e, cudaMemsetAsync(e->icp->sys, 0, sizeof(float) * 32, e->stream));
   SSF_CUDA(e, cudaMemcpyAsync(out29, e->icp->sys, 29 * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_icp_system_enqueue(SsfHandle h, const float R[9], const float t[3], int n_src, int launches) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!R || !t || launches < 0) return SSF_ERR_INVALID_ARG;
   int n = 0;
   int rc = resolve_n(e, n_src, &n);
@@ -1055,13 +1215,13 @@ int ssf_icp_system_enqueue(SsfHandle h, const float R[9], const float t[3], int 
   if (n <= 0) return SSF_ERR_STATE;
   launch_icp_set_transform(e, R, t);
   for (int i = 0; i < launches; i++) launch_icp_system(e, e->model, nullptr, n, false);
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_icp(SsfHandle h, const float* R_init, const float* t_init, float out29[29], float R_rel[9], float t_rel[3],
             int* iters, int* valid) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if ((R_init == nullptr) != (t_init == nullptr)) return SSF_ERR_INVALID_ARG;
   if (R_init) launch_icp_begin(e, R_init, t_init);
   else launch_icp_begin_from_pose(e);
@@ -1079,28 +1239,28 @@ int ssf_icp(SsfHandle h, const float* R_init, const float* t_init, float out29[2
 }
 
 int ssf_icp_begin(SsfHandle h, const float* R_init, const float* t_init) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if ((R_init == nullptr) != (t_init == nullptr)) return SSF_ERR_INVALID_ARG;
   if (R_init) launch_icp_begin(e, R_init, t_init);
   else launch_icp_begin_from_pose(e);
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_icp_build(SsfHandle h, int src_begin, int src_count, float out29[29]) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!out29 || src_begin < 0 || src_count < 0 || (src_begin & 3) || src_begin + src_count > e->cap)
     return SSF_ERR_INVALID_ARG;
   if (src_count > 0) launch_icp_build_range(e, src_begin, src_count);
   else SSF_CUDA(e, cudaMemsetAsync(e->icp->sys, 0, sizeof(float) * 32, e->stream));
   SSF_CUDA(e, cudaMemcpyAsync(out29, e->icp->sys, 29 * sizeof(float), cudaMemcpyDefault, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_icp_solve(SsfHandle h, const float sys29[29], int* done) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!sys29) return SSF_ERR_INVALID_ARG;
   int rc = ensure_scratch(e, 256);
   if (rc) return rc;
@@ -1114,7 +1274,7 @@ int ssf_icp_solve(SsfHandle h, const float sys29[29], int* done) {
 }
 
 int ssf_icp_finish(SsfHandle h, int apply_to_pose, float R_rel[9], float t_rel[3], int* iters, int* valid) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   launch_icp_finish(e, apply_to_pose != 0);
   IcpState* hs = e->h_icp;
   SSF_CUDA(e, cudaMemcpyAsync(hs, e->icp, sizeof(IcpState), cudaMemcpyDeviceToHost, e->stream));
@@ -1137,7 +1297,7 @@ int ssf_peer_handle(SsfHandle h, void* handle64) {
 }
 
 int ssf_connect_peers(SsfHandle h, int rank, int world, const void* handles) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!handles || world < 1 || world > SSF_MAX_PEERS || rank < 0 || rank >= world) return SSF_ERR_INVALID_ARG;
   float* ptrs[SSF_MAX_PEERS] = {nullptr};
   for (int g = 0; g < world; g++) {
@@ -1145,6 +1305,7 @@ int ssf_connect_peers(SsfHandle h, int rank, int world, const void* handles) {
     cudaIpcMemHandle_t hd;
     memcpy(&hd, static_cast<const char*>(handles) + (size_t)g * SSF_PEER_HANDLE_BYTES, sizeof(hd));
     void* p = nullptr;
+    if (e->xpeer_open[g]) { cudaIpcCloseMemHandle(e->xpeer_open[g]); e->xpeer_open[g] = nullptr; }   // reconnect
     SSF_CUDA(e, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
     e->xpeer_open[g] = p;
     ptrs[g] = static_cast<float*>(p);
@@ -1160,7 +1321,7 @@ int ssf_connect_peers(SsfHandle h, int rank, int world, const void* handles) {
 
 int ssf_icp_tiled(SsfHandle h, const float* R_init, const float* t_init, int src_begin, int src_count,
                   float out29[29], float R_rel[9], float t_rel[3], int* iters, int* valid) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if ((R_init == nullptr) != (t_init == nullptr)) return SSF_ERR_INVALID_ARG;
   if (src_begin < 0 || src_count < 0 || (src_begin & 3) || src_begin + src_count > e->cap) return SSF_ERR_INVALID_ARG;
   if (e->xworld < 2) return SSF_ERR_STATE;
@@ -1181,7 +1342,7 @@ int ssf_icp_tiled(SsfHandle h, const float* R_init, const float* t_init, int src
 
 int ssf_align(SsfHandle h, const SsfSurfels* source, int source_size, const float R_init[9], const float t_init[3],
               float R[9], float t[3], int* valid, int* iters, int* pairs, float out29[29]) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!source || source_size <= 0 || !R_init || !t_init || !R || !t) return SSF_ERR_INVALID_ARG;
   if (!source->positions || !source->colors || !source->orientations || !source->confidences) return SSF_ERR_INVALID_ARG;
   const size_t n = (size_t)source_size;
@@ -1210,7 +1371,7 @@ int ssf_align(SsfHandle h, const SsfSurfels* source, int source_size, const floa
   AlignResult out;
   SSF_CUDA(e, cudaMemcpyAsync(&out, res, sizeof(out), cudaMemcpyDeviceToHost, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   memcpy(R, out.R, 36);
   memcpy(t, out.t, 12);
   if (valid) *valid = out.valid;
@@ -1223,7 +1384,7 @@ int ssf_align(SsfHandle h, const SsfSurfels* source, int source_size, const floa
 int ssf_apply_deformation(SsfHandle h, const float* nodes_positions, const float* nodes_rotations,
                           const float* nodes_translations, int nb_nodes, const float* neighbours_weights,
                           const int32_t* neighbours_idx, int model_size) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!nodes_positions || !nodes_rotations || !nodes_translations || !neighbours_weights || !neighbours_idx ||
       nb_nodes <= 0 || model_size < 0 || model_size > e->cap)
     return SSF_ERR_INVALID_ARG;
@@ -1245,12 +1406,12 @@ int ssf_apply_deformation(SsfHandle h, const float* nodes_positions, const float
   SSF_CUDA(e, cudaMemcpyAsync(gt, nodes_translations, nn * 12, cudaMemcpyDefault, e->stream));
   launch_apply_deformation(e, gp, gr, gt, w, idx, model_size, nb_nodes);
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
 int ssf_get_markers(SsfHandle h, int which, float conf_thresh, float* points, float* colors, int capacity, int* count) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!points || !colors || capacity < 0 || (which != 0 && which != 1)) return SSF_ERR_INVALID_ARG;
   int n = e->S;
   if (which == 0) {
@@ -1269,7 +1430,7 @@ int ssf_get_markers(SsfHandle h, int which, float conf_thresh, float* points, fl
   SSF_CUDA(e, cudaMemcpyAsync(points, dp, (size_t)n * 72, cudaMemcpyDefault, e->stream));
   SSF_CUDA(e, cudaMemcpyAsync(colors, dc, (size_t)n * 96, cudaMemcpyDefault, e->stream));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   return SSF_OK;
 }
 
@@ -1298,7 +1459,7 @@ static void rotation_to_tf_quaternion(const float R[9], double q[4]) {
 }
 
 int ssf_format_tum_pose(SsfHandle h, const char* timestamp, char* line, size_t line_size) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   if (!timestamp || !line || line_size == 0) return SSF_ERR_INVALID_ARG;
   int rc = read_report(e, false);
   if (rc) return rc;
@@ -1313,11 +1474,11 @@ int ssf_format_tum_pose(SsfHandle h, const char* timestamp, char* line, size_t l
 }
 
 int ssf_fuse(SsfHandle h) {
-  H_CHECK(h);
+  H_CHECK_IDLE(h);
   launch_fuse(e);
   int rc = read_report(e, false);
   if (rc) return rc;
-  SSF_CUDA(e, cudaGetLastError());
+  SSF_LAUNCH_OK(e);
   fill_stats(e, 0.f);
   return SSF_OK;
 }

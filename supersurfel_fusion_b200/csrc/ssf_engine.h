@@ -112,6 +112,9 @@ struct Engine {
   int nb_stages;                          // stages = frames in flight of the pipelined mode (SSF_PIPELINE_STAGES)
   cudaEvent_t ev0, ev1, evf0, evf1;
   std::string err;
+  cudaError_t launch_err;                 // first kernel-launch failure since the last entry-point check
+  int failed;                             // a pipelined submit failed half-way: the handle refuses further work
+  int nvtx;                               // SSF_NVTX=1: NVTX ranges around the stages (host side of the enqueue)
   uint64_t launches;
 
   int W, H, S, gx, gy, cap;
@@ -193,7 +196,8 @@ inline void launch_pdl(Engine* e, void (*kernel)(P...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = e->pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kernel, P(args)...);
+  const cudaError_t rc = cudaLaunchKernelEx(&cfg, kernel, P(args)...);
+  if (rc != cudaSuccess && e->launch_err == cudaSuccess) e->launch_err = rc;   // surfaced by the entry point (launch_status)
 }
 
 // ---- stage launchers (each enqueues on e->stream, no host sync) -----------------

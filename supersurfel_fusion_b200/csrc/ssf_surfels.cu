@@ -586,6 +586,7 @@ __global__ void transform_model_kernel(SurfelSet model, const Counters* counters
   pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= counters->nb_supersurfels) return;
+  if (model.plane(P_CONF)[i] <= 0.0f) return;      // supersurfel_fusion_kernels.cu:481
   const M3 R = m3(v3(tf.R[0], tf.R[1], tf.R[2]), v3(tf.R[3], tf.R[4], tf.R[5]), v3(tf.R[6], tf.R[7], tf.R[8]));
   const V3 t = v3(tf.t[0], tf.t[1], tf.t[2]);
   stv(model, P_POS, i, R * ldv(model, P_POS, i) + t);

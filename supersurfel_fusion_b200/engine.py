@@ -59,16 +59,19 @@ class SsfFrameStats(C.Structure):
     _fields_ = [("stamp", C.c_int32), ("nb_supersurfels", C.c_int32), ("nb_visible", C.c_int32),
                 ("nb_removed", C.c_int32), ("nb_matched", C.c_int32), ("nb_inserted", C.c_int32),
                 ("icp_ran", C.c_int32), ("icp_valid", C.c_int32), ("icp_iters", C.c_int32),
-                ("icp_inliers", C.c_float), ("icp_error", C.c_double), ("gpu_ms", C.c_float)]
+                ("icp_inliers", C.c_float), ("icp_error", C.c_double), ("gpu_ms", C.c_float),
+                ("ms_ingest", C.c_float), ("ms_segmentation", C.c_float), ("ms_extraction", C.c_float),
+                ("ms_registration", C.c_float), ("ms_fusion", C.c_float)]
 
 
-SSF_FLAG_BILATERAL = 1   # include/ssf.h
+SSF_FLAG_BILATERAL = 1      # include/ssf.h
+SSF_FLAG_STAGE_TIMING = 2
 
 # every symbol include/ssf.h declares
 EXPORTS = [
     "ssf_config_default", "ssf_create", "ssf_destroy", "ssf_set_stream", "ssf_last_error", "ssf_is_initialized",
     "ssf_process_frame", "ssf_process_frame_depth16", "ssf_process_frame_device", "ssf_bilateral_filter",
-    "ssf_get_filtered_depth", "ssf_get_gray", "ssf_get_frame_stats", "ssf_submit_frame", "ssf_wait_frame", "ssf_get_pipeline_depth", "ssf_plan_pipeline", "ssf_get_model_view", "ssf_get_frame_view", "ssf_get_pose", "ssf_set_pose",
+    "ssf_get_filtered_depth", "ssf_get_gray", "ssf_get_frame_stats", "ssf_prepare", "ssf_submit_frame", "ssf_wait_frame", "ssf_get_pipeline_depth", "ssf_plan_pipeline", "ssf_get_model_view", "ssf_get_frame_view", "ssf_get_pose", "ssf_set_pose",
     "ssf_get_stamp", "ssf_set_stamp", "ssf_get_counts", "ssf_get_nb_superpixels", "ssf_copy_model",
     "ssf_copy_frame", "ssf_get_segmentation", "ssf_render_preview", "ssf_get_slanted_depth", "ssf_export_model",
     "ssf_extract_local_point_cloud", "ssf_invalidate_frame_supersurfels", "ssf_transform_model", "ssf_set_model",
@@ -104,6 +107,7 @@ def load_library():
         lib.ssf_get_filtered_depth.argtypes = [C.c_void_p, C.c_void_p]
         lib.ssf_get_gray.argtypes = [C.c_void_p, C.c_void_p]
         lib.ssf_submit_frame.argtypes = lib.ssf_process_frame.argtypes
+        lib.ssf_prepare.argtypes = [C.c_void_p, C.c_uint32]
         lib.ssf_wait_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ssf_process_frame_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         lib.ssf_tps_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
@@ -187,13 +191,13 @@ class SupersurfelFusion:
                    filter_iter=4, filter_alpha=0.1, filter_beta=1.0, filter_threshold=0.05, range_min=0.2,
                    range_max=5.0, delta_t=20, conf_thresh=2500.0, nb_supersurfels_max=50000, icp_iter=10,
                    icp_cov_thresh=0.04, nb_features=2000, features_scale_factor=1.2, features_nb_levels=8,
-                   ini_th_fast=20, min_th_fast=7, untracked_threshold=10, enable_loop_closure=False,
-                   enable_mod=False):
-        """initialize() of the reference (supersurfel_fusion.hpp:46-74).  The six sparse-VO
-        arguments are accepted and ignored (out-of-scope neighbour); loop closure and MOD
-        must stay disabled."""
-        if enable_loop_closure or enable_mod:
-            raise SsfError("enable_loop_closure / enable_mod are outside the hot path this library implements")
+                   ini_th_fast=20, min_th_fast=7, untracked_threshold=10, enable_loop_closure=True,
+                   enable_mod=True):
+        """initialize() of the reference (supersurfel_fusion.hpp:46-74), same defaults.  The six
+        sparse-VO arguments are accepted and ignored (out-of-scope neighbour); enable_loop_closure
+        and enable_mod are recorded in the configuration but not acted on: the loop detector and the
+        moving-object detector are the caller's, their results enter through align /
+        applyDeformation / setPose / transformModel / invalidateFrameSupersurfels (include/ssf.h)."""
         if self._h:
             self.close()
         cfg = SsfConfig()
@@ -210,6 +214,7 @@ class SupersurfelFusion:
         cfg.range_min, cfg.range_max = range_min, range_max
         cfg.delta_t, cfg.conf_thresh, cfg.nb_supersurfels_max = delta_t, conf_thresh, nb_supersurfels_max
         cfg.icp_iter, cfg.icp_cov_thresh = icp_iter, icp_cov_thresh
+        cfg.enable_loop_closure, cfg.enable_mod = int(bool(enable_loop_closure)), int(bool(enable_mod))
         h = C.c_void_p()
         rc = self._lib.ssf_create(C.byref(cfg), C.c_int(self._device), C.byref(h))
         if rc != SSF_OK:
@@ -221,6 +226,13 @@ class SupersurfelFusion:
         self._check(self._lib.ssf_get_nb_superpixels(self._h, C.byref(n)), "ssf_get_nb_superpixels")
         self.nbSuperpixels = n.value
         self.width, self.height = cam_param.width, cam_param.height
+        self._pending = []          # input buffers of the frames in flight (submitFrame keeps them alive)
+        return self
+
+    def prepare(self, flags=0):
+        """Build and upload every CUDA graph the given flags need before the first frame
+        (ssf_prepare): the first processFrame / submitFrame calls then cost what the later ones do."""
+        self._check(self._lib.ssf_prepare(self._h, C.c_uint32(flags)), "ssf_prepare")
         return self
 
     def close(self):
@@ -248,17 +260,7 @@ class SupersurfelFusion:
         if pose_prior is not None:
             R, t = pose_prior
             prior = np.concatenate([np.asarray(R, np.float32).reshape(9), np.asarray(t, np.float32).reshape(3)])
-        if isinstance(rgb_h, np.ndarray):
-            if rgb_h.dtype != np.uint8 or depth_h.dtype != np.float32:
-                raise SsfError("processFrame expects uint8 RGB and float32 depth")
-            if rgb_h.shape[:2] != (self.height, self.width) or depth_h.shape != (self.height, self.width):
-                raise SsfError("image size does not match the camera")
-            rs, ds = rgb_h.strides[0], depth_h.strides[0]
-            if rgb_h.strides[1:] != (3, 1) or depth_h.strides[1] != 4:
-                rgb_h, depth_h = np.ascontiguousarray(rgb_h), np.ascontiguousarray(depth_h)
-                rs, ds = rgb_h.strides[0], depth_h.strides[0]
-        else:
-            rs, ds = self.width * 3, self.width * 4
+        rgb_h, depth_h, rs, ds = self._check_images(rgb_h, depth_h, "processFrame")
         rc = self._lib.ssf_process_frame(self._h, _ptr(rgb_h), rs, _ptr(depth_h), ds, _ptr(prior), flags)
         self._check(rc, "ssf_process_frame")
         return self.getFrameStats()
@@ -278,6 +280,28 @@ class SupersurfelFusion:
                                                  float(depth_scale), _ptr(prior), flags)
         self._check(rc, "ssf_process_frame_depth16")
         return self.getFrameStats()
+
+    def processFrameStaged(self, rgb_h, depth_h, pose_prior=None, dynamic_mask=None):
+        """processFrame driven stage by stage through the stage entry points, which is how a caller
+        with a moving-object detector plugs it in: segmentation -> generateSupersurfels -> [MOD hook:
+        ssf_invalidate_frame_supersurfels(mask), what detectMotion does to frame.confidences,
+        supersurfel_fusion.cu:198-213 / motion_detection.cu:573] -> registration (+ pose composition)
+        -> fusion -> stamp + 1.  Same kernels as processFrame; depth is taken as already filtered."""
+        rgb_h = np.ascontiguousarray(rgb_h, np.uint8)
+        depth_h = np.ascontiguousarray(depth_h, np.float32)
+        self._check(self._lib.ssf_tps_segment(self._h, _ptr(rgb_h), 0, _ptr(depth_h), 0), "ssf_tps_segment")
+        self._check(self._lib.ssf_generate_supersurfels(self._h), "ssf_generate_supersurfels")
+        if dynamic_mask is not None:
+            self.invalidateFrameSupersurfels(dynamic_mask)
+        if pose_prior is not None:
+            self.setPose(*pose_prior)
+        valid, _, _, info = self.icp()
+        self.icpFinish(apply_to_pose=True)          # supersurfel_fusion.cu:313-328
+        stats = self.fuse()
+        stamp = self.getStamp()
+        self.setStamp(stamp + 1)                    # supersurfel_fusion.cu:521
+        stats.update(stamp=stamp, icp_valid=int(valid), icp_iters=info["iters"])
+        return stats
 
     # -- ingest (supersurfel_fusion.cu:171-181) -----------------------------------------
     def bilateralFilter(self, depth, kernel_size=-1, sigma_color=0.03, sigma_spatial=4.5):
@@ -300,15 +324,45 @@ class SupersurfelFusion:
         self._check(self._lib.ssf_get_gray(self._h, _ptr(out)), "ssf_get_gray")
         return out
 
+    def _check_images(self, rgb, depth, what):
+        """dtype / shape / stride checks shared by processFrame and submitFrame; returns the
+        (possibly compacted) arrays and their row strides in bytes."""
+        if isinstance(rgb, np.ndarray) != isinstance(depth, np.ndarray):
+            raise SsfError("%s: rgb and depth must both be numpy arrays or both be torch tensors" % what)
+        if isinstance(rgb, np.ndarray):
+            if rgb.dtype != np.uint8 or depth.dtype != np.float32:
+                raise SsfError("%s expects uint8 RGB and float32 depth" % what)
+            if rgb.shape != (self.height, self.width, 3) or depth.shape != (self.height, self.width):
+                raise SsfError("image size does not match the camera")
+            if rgb.strides[1:] != (3, 1) or depth.strides[1] != 4:
+                rgb, depth = np.ascontiguousarray(rgb), np.ascontiguousarray(depth)
+            return rgb, depth, rgb.strides[0], depth.strides[0]
+        if hasattr(rgb, "data_ptr"):      # torch tensors: pinned host or device memory
+            import torch
+            if rgb.dtype != torch.uint8 or depth.dtype != torch.float32:
+                raise SsfError("%s expects uint8 RGB and float32 depth" % what)
+            if tuple(rgb.shape) != (self.height, self.width, 3) or tuple(depth.shape) != (self.height, self.width):
+                raise SsfError("image size does not match the camera")
+            if not rgb.is_contiguous() or not depth.is_contiguous():
+                raise SsfError("%s: torch inputs must be contiguous" % what)
+            return rgb, depth, self.width * 3, self.width * 4
+        raise SsfError("%s: unsupported image type %r" % (what, type(rgb)))
+
     def submitFrame(self, rgb, depth, pose_prior=None, flags=0):
-        """Pipelined processFrame: enqueue and return (numpy arrays, pinned host or device torch tensors;
-        the buffers must stay alive until waitFrame() returned this frame).  Up to two frames in flight."""
+        """Pipelined processFrame: enqueue and return.  Up to pipelineDepth() frames (= pipeline
+        stages, default 4) may be in flight.  Inputs: numpy arrays or torch tensors (pinned host or
+        device), same dtype / shape / stride rules as processFrame; they are kept referenced until
+        waitFrame() has returned the frame.  Only pinned host or device memory gives an asynchronous
+        copy: with pageable numpy arrays cudaMemcpy2DAsync blocks until the copy is staged and the
+        stage-0 stream serialises behind it, so frames no longer overlap their own upload."""
         prior = None
         if pose_prior is not None:
             R, t = pose_prior
             prior = np.concatenate([np.asarray(R, np.float32).reshape(9), np.asarray(t, np.float32).reshape(3)])
-        rc = self._lib.ssf_submit_frame(self._h, _ptr(rgb), self.width * 3, _ptr(depth), self.width * 4, _ptr(prior), flags)
+        rgb, depth, rs, ds = self._check_images(rgb, depth, "submitFrame")
+        rc = self._lib.ssf_submit_frame(self._h, _ptr(rgb), rs, _ptr(depth), ds, _ptr(prior), flags)
         self._check(rc, "ssf_submit_frame")
+        self._pending.append((rgb, depth, prior))
 
     def pipelineDepth(self):
         """Frames that may be in flight through submitFrame (= pipeline stages)."""
@@ -322,6 +376,8 @@ class SupersurfelFusion:
         R = np.zeros(9, np.float32)
         t = np.zeros(3, np.float32)
         self._check(self._lib.ssf_wait_frame(self._h, C.byref(st), _ptr(R), _ptr(t)), "ssf_wait_frame")
+        if self._pending:
+            self._pending.pop(0)
         return {k: getattr(st, k) for k, _ in SsfFrameStats._fields_}, R.reshape(3, 3), t
 
     def processFrameDevice(self, rgb_dev, depth_dev, pose_prior=None, flags=0):

@@ -54,6 +54,55 @@ def test_oracle_deformation_identity_and_rigid(orc, tracked):
     assert np.abs(a.positions - (m.positions + shift)).max() < 1e-5
 
 
+def test_oracle_local_cloud_and_rigid_transform(orc, tracked):
+    """extractLocalPointCloud (supersurfel_fusion_kernels.cu:490-520) and applyTransformSuperSurfel (:467-488)
+    restatements against plain numpy in float64."""
+    eng = tracked["eng"]
+    m = eng.model()
+    R, t = eng.pose()
+    thr, radius = 300.0, 1.6
+    pos, nrm = orc.extract_local_point_cloud(m, thr, R, t, radius)
+    cam = (m.positions.astype(np.float64) - t) @ R.astype(np.float64)             # R^T (p - t), row-vector form
+    keep = (m.confidences >= thr) & (np.linalg.norm(cam, axis=1) < radius)
+    edge = np.abs(np.linalg.norm(cam, axis=1) - radius) < 1e-5                    # fp32 vs fp64 at the rim
+    assert abs(len(pos) - int(keep.sum())) <= int(edge.sum()) and len(pos) > 0 and (~keep).any()
+    if not edge.any():
+        assert np.abs(pos - cam[keep]).max() < 1e-5
+        want_n = m.orientations[keep][:, 6:9].astype(np.float64) @ R.astype(np.float64)
+        want_n /= np.linalg.norm(want_n, axis=1, keepdims=True)
+        assert np.abs(nrm - want_n).max() < 1e-5
+    assert len(eng.local_cloud(radius)[0]) == len(orc.extract_local_point_cloud(m, eng.cfg.conf_thresh, R, t, radius)[0])
+    # rigid motion: positions, orientation rows and shapes move; supersurfels with confidence <= 0 stay
+    a = orc.Surfels(m.n)
+    for name, _, _ in orc.Surfels.FIELDS:
+        getattr(a, name)[:] = getattr(m, name)
+    a.confidences[:5] = -1.0
+    Rm, tm = _rot((0.3, -1.0, 0.2), 0.4), np.array([0.1, 0.2, -0.3], np.float32)
+    orc.transform_model(a, Rm, tm)
+    assert np.array_equal(a.positions[:5], m.positions[:5]) and np.array_equal(a.shapes[:5], m.shapes[:5])
+    assert np.abs(a.positions[5:] - (m.positions[5:] @ Rm.T + tm)).max() < 1e-5
+    O = m.orientations[5:].reshape(-1, 3, 3)
+    assert np.abs(a.orientations[5:].reshape(-1, 3, 3) - O @ Rm.T).max() < 1e-5
+    def full(s):
+        return np.stack([s[:, 0], s[:, 1], s[:, 2], s[:, 1], s[:, 3], s[:, 4], s[:, 2], s[:, 4], s[:, 5]], 1).reshape(-1, 3, 3)
+    assert rel_err(full(a.shapes[5:]), Rm.astype(np.float64) @ full(m.shapes[5:]).astype(np.float64) @ Rm.T.astype(np.float64)) < 1e-5
+
+
+def test_oracle_mod_mask_blocks_fusion_and_insertion(orc):
+    """MOD hook in the oracle engine: masked frame supersurfels (confidence -1) are neither fused nor inserted."""
+    seq = SyntheticSequence(width=320, height=240, seed=9)
+    cfg = orc.default_config(cam=seq.cam_param(), **dict(TUM_PARAMS, nb_supersurfels_max=8000))
+    a, b = orc.Engine(cfg), orc.Engine(cfg)
+    for k in range(3):
+        rgb, depth = seq.frame(k)
+        sa = a.process_frame(rgb, depth)
+        mask = np.ones(a.S, np.uint8) if k == 2 else None        # everything dynamic in the last frame
+        sb = b.process_frame(rgb, depth, mask=mask)
+    assert sa["nb_matched"] > 0 and sa["nb_inserted"] >= 0
+    assert sb["nb_matched"] == 0 and sb["nb_inserted"] == 0 and sb["icp_valid"] == 0
+    assert np.all(b.frame().confidences == -1.0)
+
+
 def test_oracle_markers_and_tum_line(orc, tracked):
     m = tracked["eng"].model()
     pts, col = orc.markers(m, 300.0)
