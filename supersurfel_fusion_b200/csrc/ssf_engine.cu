@@ -118,7 +118,13 @@ struct StageRange {
 };
 // stage boundary k of a frame run with SSF_FLAG_STAGE_TIMING (an event-record node under capture)
 static void stage_mark(EngineImpl* e, bool marks, int k) {
-  if (marks) cudaEventRecord(e->ev_tm[k], e->stream);
+  if (!marks) return;
+  // under stream capture a plain cudaEventRecord only captures a dependency; the External flag makes
+  // it an event-record NODE of the graph, which is what gives a timestamp at replay
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(e->stream, &st);
+  cudaEventRecordWithFlags(e->ev_tm[k], e->stream,
+                           st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
 
 static void enqueue_steps(EngineImpl* e, int g0, int g1, bool bilateral, bool pipelined, FrameReport* report,
@@ -399,6 +405,8 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   // measured on B200 at VGA it is ~6 % slower per frame than the graph of small kernels
   // (0.602 vs 0.559 ms; per pass ~1.4 us cache fill + ~3.7 us relabel + ~1.7 us barrier for the
   // colour passes, 3.2 + 4.1 + 2.4 us with the disparity plane), see DESIGN.md section 3.
+  e->tps_fused = 1;
+  if (const char* v = getenv("SSF_TPS_FUSED")) e->tps_fused = atoi(v) != 0;   // 0: round-1 pass + merge launches (A/B)
   e->tps_persistent = 0;
   if (const char* v = getenv("SSF_TPS_PERSISTENT")) e->tps_persistent = (atoi(v) != 0 && e->tps_grid > 0) ? 1 : 0;
   e->icp_debug = 0;
@@ -416,7 +424,7 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   A(dalloc(&e->rgba, N)); A(dalloc(&e->disp, N)); A(dalloc(&e->labels, N)); A(dalloc(&e->bound, N));
   A(dalloc(&e->inliers, N)); A(dalloc(&e->lmap, N)); A(dalloc(&e->in_rgb, N * 3)); A(dalloc(&e->in_depth, N));
   A(dalloc(&e->depth_f, N)); A(dalloc(&e->in_depth16, N));
-  A(dalloc(&e->sp, (size_t)S)); A(dalloc(&e->sums, (size_t)S));
+  A(dalloc(&e->sp, (size_t)S)); A(dalloc(&e->sums, (size_t)3 * S));   // three rotating sum buffers, see ssf_tps.cu
   {
     char* p = nullptr;
     A(dalloc(&p, (size_t)S * nbs * (sizeof(float4) + sizeof(int))));
@@ -449,7 +457,7 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   for (int k = 1; k < SSF_SLOTS; k++) {
     FrameSlot& f = e->slot[k];
     A(dalloc(&f.rgba, N)); A(dalloc(&f.disp, N)); A(dalloc(&f.labels, N)); A(dalloc(&f.bound, N)); A(dalloc(&f.inliers, N));
-    A(dalloc(&f.sp, (size_t)S)); A(dalloc(&f.sums, (size_t)S));
+    A(dalloc(&f.sp, (size_t)S)); A(dalloc(&f.sums, (size_t)3 * S));
     f.frame.stride = e->frame.stride;
     A(dalloc(&f.lmap, N)); A(dalloc(&f.frame.base, (size_t)P_COUNT * e->frame.stride));
     A(dalloc(&f.ftab, (size_t)2 * S)); A(dalloc(&f.matched, (size_t)S)); A(dalloc(&f.best, (size_t)S));

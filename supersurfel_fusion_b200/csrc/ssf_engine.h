@@ -139,6 +139,7 @@ struct Engine {
   void* rng;             // curandState[S * nb_samples]
   float* filt_a;         // 8 floats per node (X, Z, px, py), double buffered
   float* filt_b;
+  int tps_fused;         // 1 (default): relabelling passes derive the means themselves, no merge launches (SSF_TPS_FUSED)
   int tps_persistent;    // 1: whole segmentation is one cooperative kernel
   int tps_grid;          // its grid (one CTA per SM)
   unsigned int* tps_barrier;   // ticket of its grid-wide barrier

@@ -48,7 +48,11 @@ struct TpsArgs {
   int* bound;
   unsigned char* inliers;
   Superpixel* sp;
-  SpSums* sums;
+  SpSums* sums;            // the sums every kernel but the fused pass works on (= sums_cur of the next pass)
+  // fused pass (tps_pass_tile_kernel): three rotating sum buffers, see there
+  SpSums* sums_nxt;
+  SpSums* sums_zero;
+  unsigned long long gx_magic;   // ceil(2^32 / gx): k / gx == (k * gx_magic) >> 32 for every superpixel id k
 };
 
 static TpsArgs tps_args(const Engine* e) {
@@ -63,8 +67,14 @@ static TpsArgs tps_args(const Engine* e) {
   a.lambda_disp = e->cfg.lambda_disp; a.thresh_disp = e->cfg.thresh_disp;
   a.rgba = e->rgba; a.disp = e->disp; a.labels = e->labels; a.bound = e->bound; a.inliers = e->inliers;
   a.sp = e->sp; a.sums = e->sums;
+  a.sums_nxt = a.sums_zero = nullptr;
+  a.gx_magic = (0x100000000ull + (unsigned)e->gx - 1) / (unsigned)e->gx;
   return a;
 }
+
+// The three rotating per-superpixel sum buffers of a frame slot: before pass p (p = passes already
+// run on this frame) the true sums are in buffer p % 3, buffer (p + 1) % 3 is all zero.
+static SpSums* sums_buffer(const Engine* e, int p) { return e->sums + (size_t)(p % 3) * e->S; }
 
 __device__ __forceinline__ void add64(long long* p, long long v) {
   atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
@@ -111,6 +121,11 @@ __global__ void __launch_bounds__(256) tps_seed_kernel(TpsArgs a, const uint8_t*
     s.x = t[0]; s.y = t[1]; s.r = t[2]; s.g = t[3]; s.b = t[4]; s.n = t[5];
     s.dx = s.dy = s.dxx = s.dyy = s.dxy = s.dn = s.dxd = s.dyd = s.dd = 0; s.pad = 0;
     a.sums[index] = s;
+    if (a.sums_nxt) {        // fused passes: the buffer the first pass accumulates into starts at zero
+      SpSums z;
+      z.x = z.y = z.r = z.g = z.b = z.n = z.dx = z.dy = z.dxx = z.dyy = z.dxy = z.dn = z.dxd = z.dyd = z.dd = z.pad = 0;
+      a.sums_nxt[index] = z;
+    }
     const float n = (float)s.n;
     Superpixel q;
     q.xy_rg = make_float4((float)s.x / n, (float)s.y / n, (float)s.r / n, (float)s.g / n);
@@ -429,6 +444,212 @@ __global__ void __launch_bounds__(128) tps_pass_kernel(TpsArgs a, int OX, int OY
   tps_pass_item<DISP>(a, src, q, ry, OX, OY);
 }
 
+// ---- one relabelling pass, merge fused in: no separate "sums -> means" launch ----------------
+// The multi-kernel form above needs a merge launch between two passes because a pass both reads
+// the per-superpixel means and changes the sums they come from.  Here a pass reads the sums of
+// the PREVIOUS pass from a quiescent buffer and accumulates its own changes into another one:
+//   before pass p:  cur = buf[p % 3] holds the true sums, nxt = buf[(p+1) % 3] is all zero;
+//   pass p:         every CTA derives the means it needs from cur (shared-memory window around
+//                   its tile; identical arithmetic to the merge kernel, so identical bits);
+//                   the CTA that owns superpixel s adds cur[s] into nxt[s] and clears
+//                   zero[s] = buf[(p+2) % 3][s] (nobody reads that buffer during pass p);
+//                   relabelled pixels add their +-deltas into nxt;
+//   after pass p:   nxt = cur + deltas = true sums.  All sums are integers: order-free, exact.
+// One thread per ACTIVE PIXEL (the pair-per-thread form halves the threads and doubles the
+// dependent chain); the two pixels of an adjacent pair are neighbouring lanes and exchange the
+// only cross-pixel quantity (the boundary-count delta each owes the other) with one shuffle.
+// The 3-row label neighbourhood of the tile is staged in shared memory with coalesced 8-byte
+// loads while the window means are being computed: one L2 round trip per pass.
+constexpr int TILE_LANES = 32;                 // active pixels per tile row (64 image columns)
+constexpr int TILE_ROWS = 8;                   // active rows per tile (16 image rows)
+constexpr int TILE_THREADS = TILE_LANES * TILE_ROWS;
+constexpr int TILE_COLS = 2 * TILE_LANES;      // image columns of a tile
+constexpr int TILE_LROWS = 2 * TILE_ROWS + 1;  // label rows staged: y0 - 1 .. y0 + 2 * TILE_ROWS - 1
+constexpr int TILE_WIN = 64;                   // capacity of the means window (superpixels)
+
+struct SpWindow {
+  const Superpixel* cache;
+  const SpSums* cur;
+  int wx0, wy0, ww, wh;      // window of grid cells [wx0, wx0 + ww) x [wy0, wy0 + wh)
+  int gx;
+  unsigned long long gx_magic;
+};
+template <bool DISP>
+struct SpTile {
+  SpWindow w;
+  __device__ __forceinline__ Superpixel get(int k) const {
+    const int cy = (int)(((unsigned long long)(unsigned)k * w.gx_magic) >> 32);
+    const int cx = k - cy * w.gx;
+    const int ux = cx - w.wx0, uy = cy - w.wy0;
+    if ((unsigned)ux < (unsigned)w.ww && (unsigned)uy < (unsigned)w.wh) return w.cache[uy * w.ww + ux];
+    return tps_superpixel_from_sums<DISP>(w.cur[k]);      // wandered out of the window: exact, just slower
+  }
+};
+
+template <bool DISP>
+__global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, int OX, int OY) {
+  pdl_sync();
+  __shared__ int lab[TILE_LROWS][TILE_COLS];
+  __shared__ Superpixel win[TILE_WIN];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, wrp = tid >> 5;
+  const SpSums* cur = a.sums;
+
+  // ---- buffer rotation for the superpixels this CTA owns
+  {
+    const int nb = gridDim.x * gridDim.y;
+    const int b = blockIdx.y * gridDim.x + blockIdx.x;
+    const int per = (a.S + nb - 1) / nb;
+    const int s0 = b * per, s1 = min(a.S, s0 + per);
+    const int words = (s1 - s0) * 16;
+    for (int i = tid; i < words; i += TILE_THREADS) {
+      const size_t off = (size_t)s0 * 16 + i;
+      const long long v = reinterpret_cast<const long long*>(cur)[off];
+      if (v != 0) add64(reinterpret_cast<long long*>(a.sums_nxt) + off, v);
+      reinterpret_cast<long long*>(a.sums_zero)[off] = 0;
+    }
+  }
+
+  // ---- geometry of the tile
+  const int q0 = blockIdx.x * (TILE_LANES / 2);          // first pair index of the tile
+  const int xs0 = 4 * q0 + (OX ? 0 : -2);                // first image column of the staged labels
+  const int ry0 = blockIdx.y * TILE_ROWS;
+  const int y0 = 2 * ry0 + OY;                           // first active row; staged rows start at y0 - 1
+
+  // ---- stage the labels (coalesced 8-byte loads; xs0 is even and W need not be)
+  for (int r = wrp; r < TILE_LROWS; r += TILE_ROWS) {
+    const int yy = y0 - 1 + r;
+    const int xx = xs0 + 2 * lane;
+    int2 v = make_int2(-1, -1);
+    if (yy >= 0 && yy < a.H) {
+      const size_t row = (size_t)yy * a.W;
+      if (xx >= 0 && xx + 1 < a.W && (((row + xx) & 1) == 0)) {
+        v = *reinterpret_cast<const int2*>(a.labels + row + xx);
+      } else {
+        if (xx >= 0 && xx < a.W) v.x = a.labels[row + xx];
+        if (xx + 1 >= 0 && xx + 1 < a.W) v.y = a.labels[row + xx + 1];
+      }
+    }
+    lab[r][2 * lane] = v.x;
+    lab[r][2 * lane + 1] = v.y;
+  }
+
+  // ---- this thread's pixel and its own inputs (in flight together with the labels)
+  const int q = q0 + (lane >> 1), j = lane & 1;
+  const int rx = (OX ? 2 * q : 2 * q - 1) + j;
+  const int ry = ry0 + wrp;
+  const int x = 2 * rx + ((rx + OX) & 1);
+  const int y = 2 * ry + OY;
+  const bool ok = ry < a.raw_h && y < a.H && 32 * (ry / 16) + OY < a.H &&
+                  rx >= 0 && rx < a.raw_w && 32 * (rx / 16) < a.W && x < a.W;
+  const size_t p = ok ? (size_t)y * a.W + x : 0;
+  PixelIn pin;
+  pin.bounds = 0; pin.col = make_uchar4(0, 0, 0, 0); pin.disp = 0.f; pin.inlier = 0;
+  if (ok) pin = tps_fetch_pixel<DISP>(a, p);
+
+  // ---- means of the superpixels around the tile, from the quiescent sums
+  SpWindow w;
+  {
+    const int px0 = max(0, xs0), px1 = min(a.W - 1, xs0 + TILE_COLS - 1);
+    const int py0 = max(0, y0 - 1), py1 = min(a.H - 1, y0 - 1 + TILE_LROWS - 1);
+    // grid cells under the tile plus a margin of one cell (boundaries drift a few pixels over the
+    // 4 * seg_iter passes); with small cells the margin, then the window itself, is cut to the
+    // capacity -- a label outside the window takes the exact fallback in SpTile::get
+    for (int m = 1; m >= 0; m--) {
+      w.wx0 = max(0, px0 / a.cell - m);
+      w.wy0 = max(0, py0 / a.cell - m);
+      w.ww = max(0, min(a.gx - 1, px1 / a.cell + m) - w.wx0 + 1);
+      w.wh = max(0, min(a.gy - 1, py1 / a.cell + m) - w.wy0 + 1);
+      if (w.ww * w.wh <= TILE_WIN) break;
+    }
+    if (w.ww * w.wh > TILE_WIN) {
+      w.wh = min(w.wh, 8);
+      w.ww = min(w.ww, TILE_WIN / w.wh);
+    }
+    w.cache = win; w.cur = cur; w.gx = a.gx; w.gx_magic = a.gx_magic;
+    const int n = w.ww * w.wh;
+    for (int i = tid; i < n; i += TILE_THREADS) {
+      const int k = (w.wy0 + i / w.ww) * a.gx + (w.wx0 + i % w.ww);
+      win[i] = tps_superpixel_from_sums<DISP>(cur[k]);
+    }
+  }
+  __syncthreads();
+
+  // ---- decide on the pass-start state
+  const int c = x - xs0;                                 // column of the pixel in the staged rows (1 .. 62 when ok)
+  Decision d;
+  d.index = d.new_index = -1; d.b = 0; d.inlier = 0; d.prev_inlier = 0;
+  float dv = 0.f;
+  int nl[4] = {-1, -1, -1, -1};
+  if (ok) {
+    int L[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) L[r][k] = lab[2 * wrp + r][c - 1 + k];
+    L[0][3] = L[1][3] = L[2][3] = -1;
+    const SpTile<DISP> src = {w};
+    tps_decide<DISP>(a, src, pin, x, y, L, 1, d, dv);
+    nl[0] = L[0][1]; nl[1] = L[1][0]; nl[2] = L[1][2]; nl[3] = L[2][1];   // up, left, right, down
+  }
+  const bool moved = ok && d.new_index != d.index;
+
+  // ---- apply.  Everything read above is pass-start state: the only pixels written in this pass
+  // are active ones, each by its own thread, and the only active 4-neighbour of an active pixel is
+  // its pair partner (the neighbouring lane).
+  int owe_partner = 0;                                   // boundary-count delta this pixel owes its partner
+  if (moved) {
+    const int nxs[4] = {0, -1, 1, 0}, nys[4] = {-1, 0, 0, 1};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int i_n = nl[k];
+      int delta = 0;
+      if (i_n == d.new_index) delta = -1;
+      else if (i_n == d.index) delta = 1;
+      if (delta == 0 || i_n == -1) continue;
+      const bool is_partner = (j == 0 && k == 2) || (j == 1 && k == 1);
+      if (is_partner) owe_partner = delta;               // delivered by the shuffle below iff the partner is live
+      else atomicAdd(&a.bound[(size_t)(y + nys[k]) * a.W + (x + nxs[k])], delta);
+    }
+    const uchar4 col = pin.col;
+    SpSums* o = &a.sums_nxt[d.index];
+    SpSums* n = &a.sums_nxt[d.new_index];
+    add64(&o->x, -x); add64(&o->y, -y); add64(&o->r, -(int)col.x); add64(&o->g, -(int)col.y);
+    add64(&o->b, -(int)col.z); add64(&o->n, -1);
+    add64(&n->x, x); add64(&n->y, y); add64(&n->r, col.x); add64(&n->g, col.y); add64(&n->b, col.z);
+    add64(&n->n, 1);
+    a.labels[p] = d.new_index;
+  }
+  if (DISP && ok) {
+    const unsigned char inl = d.inlier, was = d.prev_inlier;
+    if (inl && (!was || moved)) {
+      SpSums* s = &a.sums_nxt[d.new_index];
+      const long long qd = quantize(dv, kDispFix, kDispClamp);
+      add64(&s->dx, x); add64(&s->dy, y); add64(&s->dxx, (long long)x * x); add64(&s->dyy, (long long)y * y);
+      add64(&s->dxy, (long long)x * y); add64(&s->dxd, (long long)x * qd); add64(&s->dyd, (long long)y * qd);
+      add64(&s->dd, qd); add64(&s->dn, 1);
+    }
+    if (was && (!inl || moved)) {
+      SpSums* s = &a.sums_nxt[d.index];
+      const long long qd = quantize(dv, kDispFix, kDispClamp);
+      add64(&s->dx, -x); add64(&s->dy, -y); add64(&s->dxx, -(long long)x * x); add64(&s->dyy, -(long long)y * y);
+      add64(&s->dxy, -(long long)x * y); add64(&s->dxd, -(long long)x * qd); add64(&s->dyd, -(long long)y * qd);
+      add64(&s->dd, -qd); add64(&s->dn, -1);
+    }
+    if (inl != was) a.inliers[p] = inl;
+  }
+  // the partner's debt; a dead partner (outside the reference's thread extent) is an inactive pixel
+  // and gets its delta through the atomic path instead
+  const int partner_ok = __shfl_xor_sync(0xffffffffu, ok ? 1 : 0, 1);
+  const int from_partner = __shfl_xor_sync(0xffffffffu, owe_partner, 1);
+  if (owe_partner != 0 && !partner_ok)
+    atomicAdd(&a.bound[(size_t)y * a.W + (x + (j == 0 ? 1 : -1))], owe_partner);
+  if (ok) {
+    if (moved) a.bound[p] = d.b;                                        // own "= b" wins
+    else if (from_partner != 0) a.bound[p] = pin.bounds + from_partner; // only this thread touches it
+  }
+}
+
 // ---- RANSAC plane initialisation (TPS_RGBD_kernels.cu:318-467, 112-190) --------------
 __global__ void tps_rng_init_kernel(curandState* states, int n) {
   pdl_sync();
@@ -447,7 +668,11 @@ __device__ __forceinline__ void tps_init_sample_item(const TpsArgs& a, float4* s
                                                      curandState* states, int nbWalks, float radius, int index,
                                                      int idx) {
   curandState rnd = states[idx];
-  const float cx = a.sp[index].xy_rg.x, cy = a.sp[index].xy_rg.y;
+  // the centroid straight from the sums (what the merge kernel would have stored in a.sp: same
+  // conversions, same divisions)
+  const SpSums& sm = a.sums[index];
+  const float cn = (float)sm.n;
+  const float cx = (float)sm.x / cn, cy = (float)sm.y / cn;
   float x = cx, y = cy;
   int i = tex_label(a, x, y);
   int k = 0;
@@ -591,7 +816,8 @@ __global__ void tps_init_disp_kernel(TpsArgs a, int ransac) {
 
 // ---- plane smoothing (TPS_RGBD.cu:480-505; TPS_RGBD_kernels.cu:510-614) -----------
 // Jacobi (double buffered).  Node record: X.xyz, Z.xyz, px, py.
-__device__ __forceinline__ void tps_filter_init_item(const TpsArgs& a, float* buf, int i) {
+__device__ __forceinline__ void tps_filter_init_item(const TpsArgs& a, float* buf, int i, bool merge = false) {
+  if (merge) tps_merge_item<true>(a, i);        // fused passes: the last merge happens here
   const Superpixel s = a.sp[i];
   const float X0 = s.xy_rg.x * s.theta_b.x + s.xy_rg.y * s.theta_b.y + s.theta_b.z;
   float* n = buf + 8 * (size_t)i;
@@ -654,9 +880,9 @@ __device__ __forceinline__ void tps_filter_finish_item(const TpsArgs& a, const f
 
 // single-CTA version (multi-kernel path)
 __global__ void __launch_bounds__(1024) tps_filter_kernel(TpsArgs a, float* bufA, float* bufB, int iters, float alpha,
-                                                          float beta, float threshold) {
+                                                          float beta, float threshold, int merge) {
   pdl_sync();
-  for (int i = threadIdx.x; i < a.S; i += blockDim.x) tps_filter_init_item(a, bufA, i);
+  for (int i = threadIdx.x; i < a.S; i += blockDim.x) tps_filter_init_item(a, bufA, i, merge != 0);
   __syncthreads();
   float* cur = bufA;
   float* nxt = bufB;
@@ -906,6 +1132,7 @@ int tps_persistent_grid(int device, int gx, int gy, int cell, int height, int nb
 void launch_ingest(Engine* e, const uint8_t* rgb_dev, size_t rgb_stride, const float* depth_dev,
                    size_t depth_stride) {
   TpsArgs a = tps_args(e);
+  if (e->tps_fused && !e->tps_persistent) a.sums_nxt = sums_buffer(e, 1);   // zeroed for the first fused pass
   launch_pdl(e, tps_seed_kernel, dim3(e->S), dim3(256), 0, a, rgb_dev, rgb_stride, depth_dev, depth_stride);
   e->launches++;
 }
@@ -919,6 +1146,29 @@ static void launch_pass(Engine* e, const TpsArgs& a, int OX, int OY) {
   launch_pdl(e, tps_pass_kernel<DISP>, dim3(grd), dim3(blk), 0, a, OX, OY);
   launch_pdl(e, tps_merge_kernel<DISP>, dim3(cdiv(a.S, 128)), dim3(128), 0, a);
   e->launches += 2;
+}
+
+// pass number `p` of the frame (0 .. 4 * seg_iter - 1) in its fused form: reads buffer p % 3,
+// accumulates into (p + 1) % 3, clears (p + 2) % 3
+template <bool DISP>
+static void launch_pass_fused(Engine* e, TpsArgs a, int p, int OX, int OY) {
+  const int pairs = a.raw_w / 2 + 1;
+  a.sums = sums_buffer(e, p);
+  a.sums_nxt = sums_buffer(e, p + 1);
+  a.sums_zero = sums_buffer(e, p + 2);
+  dim3 grd(cdiv(pairs, TILE_LANES / 2), cdiv(a.raw_h, TILE_ROWS));
+  launch_pdl(e, tps_pass_tile_kernel<DISP>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY);
+  e->launches += 1;
+}
+
+template <bool DISP>
+static void launch_iteration(Engine* e, const TpsArgs& a, int first_pass) {
+  // pass order per iteration: (0,0) (1,1) (0,1) (1,0) (TPS_RGBD.cu:190-272)
+  static const int ox[4] = {0, 1, 0, 1}, oy[4] = {0, 1, 1, 0};
+  for (int k = 0; k < 4; k++) {
+    if (e->tps_fused) launch_pass_fused<DISP>(e, a, first_pass + k, ox[k], oy[k]);
+    else launch_pass<DISP>(e, a, ox[k], oy[k]);
+  }
 }
 
 // The segmentation as a sequence of steps, so that the pipelined mode can cut it anywhere between
@@ -947,20 +1197,22 @@ void launch_tps(Engine* e, int first, int last) {
     r.trace = e->tps_trace;
     cudaMemsetAsync(e->tps_barrier, 0, sizeof(unsigned int), e->stream);
     void* params[] = {&a, &r};
-    cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tps_persistent_kernel), dim3(e->tps_grid),
-                                dim3(TPS_PERSIST_THREADS), params, (size_t)e->tps_cache_slots * sizeof(Superpixel),
-                                e->stream);
+    const cudaError_t rc = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(tps_persistent_kernel), dim3(e->tps_grid),
+                                                       dim3(TPS_PERSIST_THREADS), params,
+                                                       (size_t)e->tps_cache_slots * sizeof(Superpixel), e->stream);
+    if (rc != cudaSuccess && e->launch_err == cudaSuccess) e->launch_err = rc;
     e->launches++;
     return;
   }
   const int half = nbIters / 2;
+  const bool fused = e->tps_fused != 0;
   dim3 blk(32, 8), grd(cdiv(e->W, 32), cdiv(e->H, 8));
   for (int step = first; step < last; step++) {
+    // passes already run on this frame when the step starts = which of the rotating buffers holds the sums
+    const int done = step <= half ? 4 * step : 4 * (step - 1);
+    if (fused) a.sums = sums_buffer(e, done < 4 * nbIters ? done : 4 * nbIters);
     if (step < half) {                       // colour-only iteration
-      launch_pass<false>(e, a, 0, 0);
-      launch_pass<false>(e, a, 1, 1);
-      launch_pass<false>(e, a, 0, 1);
-      launch_pass<false>(e, a, 1, 0);
+      launch_iteration<false>(e, a, done);
     } else if (step == half) {               // disparity planes: RANSAC, inlier moments, first merge
       if (e->cfg.seg_use_ransac) {
         int* votes = reinterpret_cast<int*>(e->samples + (size_t)e->S * e->cfg.nb_samples);
@@ -974,16 +1226,15 @@ void launch_tps(Engine* e, int first, int last) {
         launch_pdl(e, tps_init_disp_kernel, dim3(grd), dim3(blk), 0, a, 0);
         e->launches += 1;
       }
-      launch_pdl(e, tps_merge_kernel<true>, dim3(cdiv(a.S, 128)), dim3(128), 0, a);
-      e->launches++;
+      if (!fused) {                          // the fused passes derive means + plane from the sums themselves
+        launch_pdl(e, tps_merge_kernel<true>, dim3(cdiv(a.S, 128)), dim3(128), 0, a);
+        e->launches++;
+      }
     } else if (step <= nbIters) {            // colour + disparity iteration
-      launch_pass<true>(e, a, 0, 0);
-      launch_pass<true>(e, a, 1, 1);
-      launch_pass<true>(e, a, 0, 1);
-      launch_pass<true>(e, a, 1, 0);
+      launch_iteration<true>(e, a, done);
     } else {                                 // plane smoothing + slanted-depth render
       launch_pdl(e, tps_filter_kernel, dim3(1), dim3(1024), 0, a, e->filt_a, e->filt_b, e->cfg.filter_iter, e->cfg.filter_alpha,
-                                                   e->cfg.filter_beta, e->cfg.filter_threshold);
+                                                   e->cfg.filter_beta, e->cfg.filter_threshold, fused ? 1 : 0);
       launch_pdl(e, tps_render_kernel, dim3(grd), dim3(blk), 0, a, e->lmap);
       e->launches += 2;
     }

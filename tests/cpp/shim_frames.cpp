@@ -35,9 +35,10 @@ int main(int argc, char** argv) {
   try {
     SupersurfelFusion fusion;
     if (fusion.isInitialized()) return 3;
-    // launch/supersurfel_fusion_rgbd_benchmark.launch values, positional like the node's call
+    // launch/supersurfel_fusion_rgbd_benchmark.launch values, positional like the node's call (conf_thresh lowered
+    // so that three small frames already hold stable supersurfels for exportModel / extractLocalPointCloud)
     fusion.initialize(cam, 16, 10.0f, 1000.0f, 1000.0f, 1e8f, 1e-4f, 10, true, 16, 3, 0.1f, 1.0f, 0.05f, 0.2f, 5.0f, 20,
-                      2560.0f, 20000, 10, 0.05);
+                      400.0f, 20000, 10, 0.05);
     if (!fusion.isInitialized()) return 4;
     std::vector<uint8_t> rgb((size_t)W * H * 3);
     std::vector<float> depth((size_t)W * H);

@@ -34,7 +34,7 @@ def test_cpp_shim_runs_frames_and_matches_ctypes(ssf_lib_path, tmp_path):
     rows = [l.split() for l in out.stdout.splitlines()]
     poses = {int(r[1]): np.array([float(v) for v in r[2:]], np.float32) for r in rows if r[0] == "pose"}
     stats = {int(r[1]): [int(v) for v in r[2:]] for r in rows if r[0] == "stats"}
-    eng = SupersurfelFusion().initialize(CamParam(*cam), **dict(TUM_PARAMS, nb_supersurfels_max=20000, seg_use_ransac=True))
+    eng = SupersurfelFusion().initialize(CamParam(*cam), **dict(TUM_PARAMS, nb_supersurfels_max=20000, seg_use_ransac=True, conf_thresh=400.0))
     for k, (rgb, depth) in enumerate(frames):
         st = eng.processFrame(rgb, depth)
         R, t = eng.getPose()
