@@ -53,6 +53,7 @@ struct TpsArgs {
   SpSums* sums_nxt;
   SpSums* sums_zero;
   unsigned long long gx_magic;   // ceil(2^32 / gx): k / gx == (k * gx_magic) >> 32 for every superpixel id k
+  unsigned long long cell_magic; // ceil(2^32 / cell), the same for pixel coordinates
 };
 
 static TpsArgs tps_args(const Engine* e) {
@@ -69,6 +70,7 @@ static TpsArgs tps_args(const Engine* e) {
   a.sp = e->sp; a.sums = e->sums;
   a.sums_nxt = a.sums_zero = nullptr;
   a.gx_magic = (0x100000000ull + (unsigned)e->gx - 1) / (unsigned)e->gx;
+  a.cell_magic = (0x100000000ull + (unsigned)e->cfg.cell_size - 1) / (unsigned)e->cfg.cell_size;
   return a;
 }
 
@@ -486,6 +488,11 @@ struct SpTile {
   }
 };
 
+// a / d for 0 <= a < 2^16 by the multiplier ceil(2^32 / d) (exact while a * d < 2^32)
+__device__ __forceinline__ int div_magic(int a, unsigned long long magic) {
+  return (int)(((unsigned long long)(unsigned)a * magic) >> 32);
+}
+
 template <bool DISP>
 __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, int OX, int OY) {
   pdl_sync();
@@ -495,20 +502,9 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
   const int lane = tid & 31, wrp = tid >> 5;
   const SpSums* cur = a.sums;
 
-  // ---- buffer rotation for the superpixels this CTA owns
-  {
-    const int nb = gridDim.x * gridDim.y;
-    const int b = blockIdx.y * gridDim.x + blockIdx.x;
-    const int per = (a.S + nb - 1) / nb;
-    const int s0 = b * per, s1 = min(a.S, s0 + per);
-    const int words = (s1 - s0) * 16;
-    for (int i = tid; i < words; i += TILE_THREADS) {
-      const size_t off = (size_t)s0 * 16 + i;
-      const long long v = reinterpret_cast<const long long*>(cur)[off];
-      if (v != 0) add64(reinterpret_cast<long long*>(a.sums_nxt) + off, v);
-      reinterpret_cast<long long*>(a.sums_zero)[off] = 0;
-    }
-  }
+  // The kernel is a chain of dependent latencies (L2 round trip -> means -> decisions -> atomics), so
+  // it is written to have every global load of the pass in flight before anything waits: first the
+  // sums behind the means window, then the label rows, then the pixel's own inputs.
 
   // ---- geometry of the tile
   const int q0 = blockIdx.x * (TILE_LANES / 2);          // first pair index of the tile
@@ -516,12 +512,64 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
   const int ry0 = blockIdx.y * TILE_ROWS;
   const int y0 = 2 * ry0 + OY;                           // first active row; staged rows start at y0 - 1
 
-  // ---- stage the labels (coalesced 8-byte loads; xs0 is even and W need not be)
-  for (int r = wrp; r < TILE_LROWS; r += TILE_ROWS) {
+  // ---- window of superpixels whose means this tile may need: the grid cells under the tile plus a
+  // margin of one cell (boundaries drift a few pixels over the 4 * seg_iter passes); with small
+  // cells the margin, then the window itself, is cut to the capacity -- a label outside the window
+  // takes the exact fallback in SpTile::get
+  SpWindow w;
+  {
+    const int px0 = max(0, xs0), px1 = min(a.W - 1, xs0 + TILE_COLS - 1);
+    const int py0 = max(0, y0 - 1), py1 = min(a.H - 1, y0 - 1 + TILE_LROWS - 1);
+    const int cx0 = div_magic(px0, a.cell_magic), cx1 = div_magic(px1, a.cell_magic);
+    const int cy0 = div_magic(py0, a.cell_magic), cy1 = div_magic(py1, a.cell_magic);
+#pragma unroll
+    for (int m = 1; m >= 0; m--) {
+      w.wx0 = max(0, cx0 - m);
+      w.wy0 = max(0, cy0 - m);
+      w.ww = max(0, min(a.gx - 1, cx1 + m) - w.wx0 + 1);
+      w.wh = max(0, min(a.gy - 1, cy1 + m) - w.wy0 + 1);
+      if (w.ww * w.wh <= TILE_WIN) break;
+    }
+    if (w.ww * w.wh > TILE_WIN) {
+      w.wh = min(w.wh, 8);
+      w.ww = min(w.ww, TILE_WIN / w.wh);
+    }
+    w.cache = win; w.cur = cur; w.gx = a.gx; w.gx_magic = a.gx_magic;
+  }
+  // thread i < n computes the means of window slot i (with DISP, thread TILE_WIN + i its plane)
+  const int nwin = w.ww * w.wh;
+  const int slot = tid & (TILE_WIN - 1);
+  const bool does_mean = tid < TILE_WIN && slot < nwin;
+  const bool does_plane = DISP && tid >= TILE_WIN && tid < 2 * TILE_WIN && slot < nwin;
+  int wk = 0;
+  if (does_mean || does_plane) {
+    const int wr = (int)(((float)slot + 0.5f) * __frcp_rn((float)w.ww));     // slot / ww, exact for these sizes
+    wk = (w.wy0 + wr) * a.gx + (w.wx0 + (slot - wr * w.ww));
+  }
+  // 16-byte loads of the half of the record this thread needs
+  longlong2 sv[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) sv[k] = make_longlong2(0, 0);
+  {
+    const longlong2* rec = reinterpret_cast<const longlong2*>(cur + wk);
+    if (does_mean) {                       // x y | r g | b n
+#pragma unroll
+      for (int k = 0; k < 3; k++) sv[k] = rec[k];
+    } else if (does_plane) {               // dx dy | dxx dyy | dxy dn | dxd dyd | dd pad
+#pragma unroll
+      for (int k = 0; k < 5; k++) sv[k] = rec[3 + k];
+    }
+  }
+
+  // ---- label rows (coalesced 8-byte loads; xs0 is even and W need not be): all in flight, stored later
+  int2 lv[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int r = wrp + k * TILE_ROWS;
     const int yy = y0 - 1 + r;
     const int xx = xs0 + 2 * lane;
     int2 v = make_int2(-1, -1);
-    if (yy >= 0 && yy < a.H) {
+    if (r < TILE_LROWS && yy >= 0 && yy < a.H) {
       const size_t row = (size_t)yy * a.W;
       if (xx >= 0 && xx + 1 < a.W && (((row + xx) & 1) == 0)) {
         v = *reinterpret_cast<const int2*>(a.labels + row + xx);
@@ -530,11 +578,10 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
         if (xx + 1 >= 0 && xx + 1 < a.W) v.y = a.labels[row + xx + 1];
       }
     }
-    lab[r][2 * lane] = v.x;
-    lab[r][2 * lane + 1] = v.y;
+    lv[k] = v;
   }
 
-  // ---- this thread's pixel and its own inputs (in flight together with the labels)
+  // ---- this thread's pixel and its own inputs
   const int q = q0 + (lane >> 1), j = lane & 1;
   const int rx = (OX ? 2 * q : 2 * q - 1) + j;
   const int ry = ry0 + wrp;
@@ -547,31 +594,34 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
   pin.bounds = 0; pin.col = make_uchar4(0, 0, 0, 0); pin.disp = 0.f; pin.inlier = 0;
   if (ok) pin = tps_fetch_pixel<DISP>(a, p);
 
-  // ---- means of the superpixels around the tile, from the quiescent sums
-  SpWindow w;
-  {
-    const int px0 = max(0, xs0), px1 = min(a.W - 1, xs0 + TILE_COLS - 1);
-    const int py0 = max(0, y0 - 1), py1 = min(a.H - 1, y0 - 1 + TILE_LROWS - 1);
-    // grid cells under the tile plus a margin of one cell (boundaries drift a few pixels over the
-    // 4 * seg_iter passes); with small cells the margin, then the window itself, is cut to the
-    // capacity -- a label outside the window takes the exact fallback in SpTile::get
-    for (int m = 1; m >= 0; m--) {
-      w.wx0 = max(0, px0 / a.cell - m);
-      w.wy0 = max(0, py0 / a.cell - m);
-      w.ww = max(0, min(a.gx - 1, px1 / a.cell + m) - w.wx0 + 1);
-      w.wh = max(0, min(a.gy - 1, py1 / a.cell + m) - w.wy0 + 1);
-      if (w.ww * w.wh <= TILE_WIN) break;
+  // ---- means (and planes) of the window from the quiescent sums: the merge kernel's arithmetic,
+  // split over two threads per superpixel so that the divisions of the means and the dependent
+  // divisions of the plane solve run side by side
+  if (does_mean) {
+    const float n = (float)sv[2].y;
+    Superpixel& s = win[slot];
+    s.xy_rg = make_float4((float)sv[0].x / n, (float)sv[0].y / n, (float)sv[1].x / n, (float)sv[1].y / n);
+    s.size = make_float4(n, 0.f, 0.f, 0.f);
+    const float mb = (float)sv[2].x / n;
+    if (DISP) s.theta_b.w = mb;
+    else s.theta_b = make_float4(0.f, 0.f, 0.f, mb);
+  } else if (does_plane) {
+    const float dx = (float)sv[0].x, dy = (float)sv[0].y, dxx = (float)sv[1].x, dyy = (float)sv[1].y,
+                dxy = (float)sv[2].x, dn = (float)sv[2].y;
+    const float dxd = (float)((double)sv[3].x * (1.0 / kDispFix));
+    const float dyd = (float)((double)sv[3].y * (1.0 / kDispFix));
+    const float dd = (float)((double)sv[4].x * (1.0 / kDispFix));
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    if (!solve_plane(tx, ty, tz, dxx, dxy, dx, dxd, dxy, dyy, dy, dyd, dx, dy, dn, dd)) {
+      tx = 0.f; ty = 0.f; tz = __int_as_float(0xFFE00000);
     }
-    if (w.ww * w.wh > TILE_WIN) {
-      w.wh = min(w.wh, 8);
-      w.ww = min(w.ww, TILE_WIN / w.wh);
-    }
-    w.cache = win; w.cur = cur; w.gx = a.gx; w.gx_magic = a.gx_magic;
-    const int n = w.ww * w.wh;
-    for (int i = tid; i < n; i += TILE_THREADS) {
-      const int k = (w.wy0 + i / w.ww) * a.gx + (w.wx0 + i % w.ww);
-      win[i] = tps_superpixel_from_sums<DISP>(cur[k]);
-    }
+    Superpixel& s = win[slot];
+    s.theta_b.x = tx; s.theta_b.y = ty; s.theta_b.z = tz;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int r = wrp + k * TILE_ROWS;
+    if (r < TILE_LROWS) *reinterpret_cast<int2*>(&lab[r][2 * lane]) = lv[k];
   }
   __syncthreads();
 
@@ -647,6 +697,21 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
   if (ok) {
     if (moved) a.bound[p] = d.b;                                        // own "= b" wins
     else if (from_partner != 0) a.bound[p] = pin.bounds + from_partner; // only this thread touches it
+  }
+
+  // ---- buffer rotation for the superpixels this CTA owns (last: nothing waits for it)
+  {
+    const int nb = gridDim.x * gridDim.y;
+    const int b = blockIdx.y * gridDim.x + blockIdx.x;
+    const int per = (a.S + nb - 1) / nb;
+    const int s0 = b * per, s1 = min(a.S, s0 + per);
+    const int words = (s1 - s0) * 16;
+    for (int i = tid; i < words; i += TILE_THREADS) {
+      const size_t off = (size_t)s0 * 16 + i;
+      const long long v = reinterpret_cast<const long long*>(cur)[off];
+      if (v != 0) add64(reinterpret_cast<long long*>(a.sums_nxt) + off, v);
+      reinterpret_cast<long long*>(a.sums_zero)[off] = 0;
+    }
   }
 }
 

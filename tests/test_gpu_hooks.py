@@ -14,9 +14,8 @@ from supersurfel_fusion_b200.synth import SyntheticSequence
 pytestmark = pytest.mark.gpu
 
 
-def _rows_sorted(a):
-    a = np.asarray(a)
-    return a[np.lexsort(np.round(a, 4).T[::-1])] if len(a) else a
+def _row_order(a):
+    return np.lexsort(np.round(np.asarray(a), 4).T[::-1])
 
 
 def _rot(axis, ang):
@@ -93,9 +92,10 @@ def test_local_point_cloud_matches_oracle(orc):
         po, no = oeng.local_cloud(r)
         pg, ng = geng.extractLocalPointCloud(radius)
         assert len(pg) == len(po) > 0, (radius, len(pg), len(po))
-        # the reference appends by atomic ticket: compare as sets of rows
-        assert np.abs(_rows_sorted(pg) - _rows_sorted(po)).max() < 1e-5
-        assert np.abs(_rows_sorted(ng) - _rows_sorted(no)).max() < 1e-5
+        # the reference appends by atomic ticket: compare as sets of rows, paired by position
+        og, oo = _row_order(pg), _row_order(po)
+        assert np.abs(pg[og] - po[oo]).max() < 1e-5
+        assert np.abs(ng[og] - no[oo]).max() < 1e-5
         assert np.all(np.linalg.norm(pg, axis=1) < r)
         assert np.abs(np.linalg.norm(ng, axis=1) - 1.0).max() < 1e-5
     assert len(geng.extractLocalPointCloud(None)[0]) <= stable
