@@ -192,6 +192,9 @@ int ssf_get_pipeline_depth(SsfHandle h, int* stages);
  * extraction, T + 2 = registration + fusion; stage p runs steps [first[p], first[p + 1]).
  * first must hold stages + 1 ints.  Returns the number of stages used (>= 1), *nb_steps = T + 3. */
 int ssf_plan_pipeline(const SsfConfig* cfg, int stages, int persistent_segmentation, int* first, int* nb_steps);
+/* The per-step cost estimates (microseconds on a B200 at 640x480; only their ratios matter) that
+ * ssf_plan_pipeline balances.  Writes one int per frame step, returns the number of steps. */
+int ssf_plan_weights(const SsfConfig* cfg, int persistent_segmentation, int* weights, int capacity);
 
 /* ---- ingest (supersurfel_fusion.cu:171-181) -------------------------------- */
 /* cv::cuda::bilateralFilter(depth, depth, kernel_size, sigma_color, sigma_spatial)

@@ -20,6 +20,7 @@ namespace ssf {
 
 void launch_icp_set_transform(Engine* e, const float* R, const float* t);
 size_t tps_rng_state_bytes();
+void tps_configure();
 size_t tps_trace_bytes(int grid);
 int tps_persistent_grid(int device, int gx, int gy, int cell, int height, int nb_iters, int* cache_slots);
 
@@ -62,9 +63,10 @@ struct EngineImpl : public SsfEngine {
   // nb_stages contiguous stages (stage_first[p] .. stage_first[p+1]); per slot and stage one CUDA
   // graph (two for the stage that holds the ingest: with / without the bilateral filter)
   int stage_first[SSF_SLOTS + 1];
-  cudaGraphExec_t stage_graph[SSF_SLOTS][SSF_SLOTS][2];
-  bool stage_ready[SSF_SLOTS][SSF_SLOTS][2];
-  uint64_t stage_launches[SSF_SLOTS][SSF_SLOTS][2];
+  // variant of a stage graph: bit 0 = bilateral ingest (first stage), bit 1 = one-launch registration (last stage)
+  cudaGraphExec_t stage_graph[SSF_SLOTS][SSF_SLOTS][4];
+  bool stage_ready[SSF_SLOTS][SSF_SLOTS][4];
+  uint64_t stage_launches[SSF_SLOTS][SSF_SLOTS][4];
   cudaEvent_t ev_stage[SSF_SLOTS][SSF_SLOTS], ev_done[SSF_SLOTS], ev_t0[SSF_SLOTS], ev_t1[SSF_SLOTS];
   FrameReport* d_report2[SSF_SLOTS];
   FrameReport* h_report2[SSF_SLOTS];
@@ -72,13 +74,14 @@ struct EngineImpl : public SsfEngine {
   int pipe_next;     // slot of the next submitted frame
   int pipe_oldest;   // slot of the oldest frame in flight
   int in_flight;
-  uint64_t launches_per_frame[4];
+  uint64_t launches_per_frame[8];
   cudaEvent_t ev_tm[6];            // stage boundaries of a frame run with SSF_FLAG_STAGE_TIMING
   FrameReport* d_report;
   FrameReport* h_report;
   float* h_prior;          // pinned 12 floats
-  cudaGraphExec_t graph_exec[4];   // bit 0: SSF_FLAG_BILATERAL, bit 1: SSF_FLAG_STAGE_TIMING (event nodes at stage boundaries)
-  bool graph_ready[4];
+  // bit 0: SSF_FLAG_BILATERAL, bit 1: SSF_FLAG_STAGE_TIMING (event nodes at stage boundaries), bit 2: one-launch registration
+  cudaGraphExec_t graph_exec[8];
+  bool graph_ready[8];
   bool use_graph;
   bool created;
 };
@@ -107,7 +110,7 @@ static void select_slot(EngineImpl* e, int s) {
 
 // The frame as a sequence of steps: 0 = ingest, 1 .. T = the segmentation steps (tps_step_count),
 // T + 1 = extraction, T + 2 = registration + fusion.  enqueue_steps enqueues [g0, g1).
-static void enqueue_track(EngineImpl* e, FrameReport* report, int advance, bool marks);
+static void enqueue_track(EngineImpl* e, FrameReport* report, int advance, bool marks, bool small);
 
 // NVTX range on the host side of the enqueue (SSF_NVTX=1): shows the stage structure of a frame
 // in a timeline next to the kernels; under graph replay only the capture carries the ranges.
@@ -128,7 +131,7 @@ static void stage_mark(EngineImpl* e, bool marks, int k) {
 }
 
 static void enqueue_steps(EngineImpl* e, int g0, int g1, bool bilateral, bool pipelined, FrameReport* report,
-                          bool marks = false) {
+                          bool marks = false, bool small = false) {
   const int T = tps_step_count(e);
   if (g0 <= 0) stage_mark(e, marks, 0);
   if (g0 <= 0 && g1 > 0) {
@@ -156,7 +159,7 @@ static void enqueue_steps(EngineImpl* e, int g0, int g1, bool bilateral, bool pi
       e->launches++;
     }
   }
-  if (g0 <= T + 2 && g1 > T + 2) enqueue_track(e, report, pipelined ? 1 : 3, marks);
+  if (g0 <= T + 2 && g1 > T + 2) enqueue_track(e, report, pipelined ? 1 : 3, marks, small);
 }
 
 // Cut the frame's steps (0 = ingest, 1 .. T = segmentation steps, T + 1 = extraction, T + 2 =
@@ -164,21 +167,32 @@ static void enqueue_steps(EngineImpl* e, int g0, int g1, bool bilateral, bool pi
 // kernel launches of a step, the quantity that sets a stage's duration at VGA.  Pure function of
 // the configuration (also behind ssf_plan_pipeline for the CPU tests); writes first[0 .. used]
 // and returns the number of stages used.
+// Cost of frame step g in microseconds on a B200 at 640x480 (round-2 measurements, profiles/launches_r2_*.txt:
+// the fused relabelling passes run ~4.5 / ~5.5 us each, four per iteration; the one-launch registration ~3 us
+// per Gauss-Newton iteration).  Only the ratios matter; at other frame sizes they stay roughly the same.
+static int step_weight(int g, int seg_iter, int icp_iter, int persistent) {
+  const int T = persistent ? 1 : seg_iter + 2, half = seg_iter / 2;
+  if (g == 0) return 8;                                   // ingest
+  if (g <= T) {
+    const int t = g - 1;
+    if (persistent) return 300;
+    if (t < half) return 18;                              // colour-only iteration
+    if (t == half) return 38;                             // RANSAC + inlier moments
+    if (t <= seg_iter) return 22;                         // colour + disparity iteration
+    return 12;                                            // smoothing + render
+  }
+  if (g == T + 1) return 20;                              // extraction
+  return 40 + 3 * icp_iter;                               // registration + fusion
+}
+
 static int plan_stages_impl(int seg_iter, int icp_iter, int persistent, int stages, int* first) {
-  const int T = persistent ? 1 : seg_iter + 2, G = T + 3, half = seg_iter / 2;
+  const int T = persistent ? 1 : seg_iter + 2, G = T + 3;
   if (stages < 1) stages = 1;
   if (stages > SSF_SLOTS) stages = SSF_SLOTS;
   if (stages > G) stages = G;
   if (G > 64) { first[0] = 0; first[1] = G; return 1; }      // absurd iteration counts: no pipelining
   int w[64];
-  for (int g = 0; g < G; g++) {
-    if (g == 0) w[g] = 3;
-    else if (g <= T) {
-      const int t = g - 1;
-      w[g] = persistent ? 60 : (t < half ? 8 : (t == half ? 6 : (t <= seg_iter ? 10 : 3)));
-    } else if (g == T + 1) w[g] = 3;
-    else w[g] = 12 + icp_iter;
-  }
+  for (int g = 0; g < G; g++) w[g] = step_weight(g, seg_iter, icp_iter, persistent);
   // dynamic programme: best[p][g] = minimal heaviest group when the first g steps form p groups
   static const int INF = 1 << 28;
   int best[SSF_SLOTS + 1][65], cut[SSF_SLOTS + 1][65];
@@ -209,12 +223,16 @@ static void enqueue_seg(EngineImpl* e, bool bilateral, bool marks) {
 }
 
 // stage C: registration + fusion (reads the slot's hand-over set, owns pose / model / counters)
-static void enqueue_track(EngineImpl* e, FrameReport* report, int advance, bool marks) {
+static void enqueue_track(EngineImpl* e, FrameReport* report, int advance, bool marks, bool small) {
   {
     StageRange r(e, "ssf:registration");
-    launch_icp_begin_from_pose(e);
-    launch_icp_loop(e);
-    launch_icp_finish(e, true);
+    if (small) {
+      launch_icp_registration_loop(e, true);      // begin + Gauss-Newton loop + finish: one cluster launch
+    } else {
+      launch_icp_begin_from_pose(e);
+      launch_icp_loop(e);
+      launch_icp_finish(e, true);
+    }
     stage_mark(e, marks, 4);
   }
   StageRange r(e, "ssf:fusion");
@@ -224,9 +242,34 @@ static void enqueue_track(EngineImpl* e, FrameReport* report, int advance, bool 
   stage_mark(e, marks, 5);
 }
 
-static void enqueue_frame(EngineImpl* e, bool bilateral, bool marks) {
+static void enqueue_frame(EngineImpl* e, bool bilateral, bool marks, bool small) {
   enqueue_seg(e, bilateral, marks);
-  enqueue_track(e, e->d_report, 3, marks);
+  enqueue_track(e, e->d_report, 3, marks, small);
+}
+
+// Whether a registration over about `n_visible` model supersurfels should take the one-launch path.
+// Purely a performance choice: where it is allowed at all (icp_loop_equivalent) the two paths give
+// identical bits, so a stale estimate only costs time.
+static bool pick_small_icp(const EngineImpl* e, long long n_visible) {
+  return e->icp_loop && icp_loop_equivalent(e) && n_visible <= (long long)icp_loop_max_sources();
+}
+
+// the synchronous frame graph of variant gi (bit 0 bilateral, bit 1 stage timing, bit 2 one-launch registration)
+static int ensure_frame_graph(EngineImpl* e, int gi, bool upload) {
+  if (e->graph_ready[gi]) return SSF_OK;
+  if (e->cur_slot != 0) select_slot(e, 0);
+  cudaGraph_t g;
+  const uint64_t before = e->launches;
+  SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  enqueue_frame(e, (gi & 1) != 0, (gi & 2) != 0, (gi & 4) != 0);
+  SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
+  e->launches_per_frame[gi] = e->launches - before;
+  e->launches = before;
+  SSF_CUDA(e, cudaGraphInstantiate(&e->graph_exec[gi], g, 0));
+  cudaGraphDestroy(g);
+  e->graph_ready[gi] = true;
+  if (upload) SSF_CUDA(e, cudaGraphUpload(e->graph_exec[gi], e->stream));
+  return SSF_OK;
 }
 
 static int ensure_scratch(EngineImpl* e, size_t bytes) {
@@ -377,7 +420,7 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   e->failed = 0;
   e->nvtx = 0;
   if (const char* v = getenv("SSF_NVTX")) e->nvtx = atoi(v) != 0;
-  for (int k = 0; k < 4; k++) e->graph_ready[k] = false;
+  for (int k = 0; k < 8; k++) e->graph_ready[k] = false;
   e->use_graph = true;
   e->created = false;
   e->W = cfg->cam.width; e->H = cfg->cam.height;
@@ -400,6 +443,7 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   e->icp_stages = 1;
   if (const char* v = getenv("SSF_ICP_STAGES")) e->icp_stages = atoi(v);   // tuning knob: 1 (no ring) .. 4
   e->icp_stages = icp_configure(e->icp_stages);
+  tps_configure();
   e->tps_grid = tps_persistent_grid(device, e->gx, e->gy, cfg->cell_size, e->H, cfg->seg_iter, &e->tps_cache_slots);
   // The one-kernel (cooperative, band-owned) form of the segmentation is kept as an option:
   // measured on B200 at VGA it is ~6 % slower per frame than the graph of small kernels
@@ -411,6 +455,8 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   if (const char* v = getenv("SSF_TPS_PERSISTENT")) e->tps_persistent = (atoi(v) != 0 && e->tps_grid > 0) ? 1 : 0;
   e->icp_debug = 0;
   if (const char* v = getenv("SSF_ICP_DEBUG")) e->icp_debug = atoi(v);
+  e->icp_loop = 1;
+  if (const char* v = getenv("SSF_ICP_LOOP")) e->icp_loop = atoi(v) != 0;   // 0: always the multi-launch registration (A/B)
   e->icp_grid = need_blocks < e->icp_occ * sms ? need_blocks : e->icp_occ * sms;
 
   cudaError_t err = cudaSuccess;
@@ -511,14 +557,14 @@ int ssf_destroy(SsfHandle h) {
   EngineImpl* e = static_cast<EngineImpl*>(h);
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
-  for (int k = 0; k < 4; k++)
+  for (int k = 0; k < 8; k++)
     if (e->graph_ready[k]) cudaGraphExecDestroy(e->graph_exec[k]);
   for (int k = 0; k < 6; k++)
     if (e->ev_tm[k]) cudaEventDestroy(e->ev_tm[k]);
   if (e->slot[0].lmap) select_slot(e, 0);
   for (int k = 0; k < SSF_SLOTS; k++) {
     for (int p = 0; p < SSF_SLOTS; p++) {
-      for (int b = 0; b < 2; b++)
+      for (int b = 0; b < 4; b++)
         if (e->stage_ready[k][p][b]) cudaGraphExecDestroy(e->stage_graph[k][p][b]);
       if (e->ev_stage[k][p]) cudaEventDestroy(e->ev_stage[k][p]);
     }
@@ -562,11 +608,11 @@ int ssf_set_stream(SsfHandle h, void* cuda_stream) {
   if (e->in_flight) { e->err = "pipelined frames in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
-  for (int k = 0; k < 4; k++)
+  for (int k = 0; k < 8; k++)
     if (e->graph_ready[k]) { cudaGraphExecDestroy(e->graph_exec[k]); e->graph_ready[k] = false; }
   for (int k = 0; k < SSF_SLOTS; k++)
     for (int p = 0; p < SSF_SLOTS; p++)
-      for (int b = 0; b < 2; b++)
+      for (int b = 0; b < 4; b++)
         if (e->stage_ready[k][p][b]) { cudaGraphExecDestroy(e->stage_graph[k][p][b]); e->stage_ready[k][p][b] = false; }
   return SSF_OK;
 }
@@ -580,7 +626,8 @@ int ssf_is_initialized(SsfHandle h) { return (h && static_cast<EngineImpl*>(h)->
 
 static int run_frame(EngineImpl* e, const float* prior, uint32_t flags) {
   const bool marks = (flags & SSF_FLAG_STAGE_TIMING) != 0;
-  const int gi = ((flags & SSF_FLAG_BILATERAL) ? 1 : 0) | (marks ? 2 : 0);
+  const bool small = pick_small_icp(e, e->h_report->counters.nb_visible);   // what the last report saw
+  const int gi = ((flags & SSF_FLAG_BILATERAL) ? 1 : 0) | (marks ? 2 : 0) | (small ? 4 : 0);
   if (e->in_flight) { e->err = "synchronous frame while pipelined frames are in flight: ssf_wait_frame first"; return SSF_ERR_STATE; }
   if (e->cur_slot != 0) select_slot(e, 0);
   if (prior) {
@@ -589,22 +636,14 @@ static int run_frame(EngineImpl* e, const float* prior, uint32_t flags) {
   }
   SSF_CUDA(e, cudaEventRecord(e->evf0, e->stream));
   if (e->use_graph) {
-    if (!e->graph_ready[gi]) {
-      cudaGraph_t g;
-      const uint64_t before = e->launches;
-      SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-      enqueue_frame(e, (gi & 1) != 0, marks);
-      SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
-      e->launches_per_frame[gi] = e->launches - before;
-      e->launches = before;
-      SSF_CUDA(e, cudaGraphInstantiate(&e->graph_exec[gi], g, 0));
-      cudaGraphDestroy(g);
-      e->graph_ready[gi] = true;
+    {
+      const int rc = ensure_frame_graph(e, gi, false);
+      if (rc) return rc;
     }
     SSF_CUDA(e, cudaGraphLaunch(e->graph_exec[gi], e->stream));
     e->launches += e->launches_per_frame[gi];
   } else {
-    enqueue_frame(e, (gi & 1) != 0, marks);
+    enqueue_frame(e, (gi & 1) != 0, marks, small);
   }
   SSF_CUDA(e, cudaEventRecord(e->evf1, e->stream));
   SSF_CUDA(e, cudaMemcpyAsync(e->h_report, e->d_report, sizeof(FrameReport), cudaMemcpyDeviceToHost, e->stream));
@@ -701,7 +740,7 @@ static int capture_stage(EngineImpl* e, int slot, int stage, int gi) {
   cudaGraph_t g;
   const uint64_t before = e->launches;
   SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-  enqueue_steps(e, e->stage_first[stage], e->stage_first[stage + 1], gi != 0, true, e->d_report2[slot]);
+  enqueue_steps(e, e->stage_first[stage], e->stage_first[stage + 1], (gi & 1) != 0, true, e->d_report2[slot], false, (gi & 2) != 0);
   SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
   e->stage_launches[slot][stage][gi] = e->launches - before;
   e->launches = before;
@@ -711,13 +750,18 @@ static int capture_stage(EngineImpl* e, int slot, int stage, int gi) {
   return SSF_OK;
 }
 
+// variant of the graph of stage p for these frame flags / registration path
+static int stage_variant(const EngineImpl* e, int p, uint32_t flags, bool small) {
+  return ((p == 0 && (flags & SSF_FLAG_BILATERAL)) ? 1 : 0) | ((p == e->nb_stages - 1 && small) ? 2 : 0);
+}
+
 // Everything of ssf_submit_frame that can fail after work was enqueued; see the caller.
 static int submit_enqueue(EngineImpl* e, int s, const uint8_t* rgb, size_t rgb_stride, const float* depth,
-                          size_t depth_stride, const float* pose_prior_Rt12, uint32_t flags) {
+                          size_t depth_stride, const float* pose_prior_Rt12, uint32_t flags, bool small) {
   const int P = e->nb_stages;
   for (int p = 0; p < P; p++) {
     cudaStream_t st = p == 0 ? e->stream : e->stage_stream[p];
-    const int gi = (p == 0 && (flags & SSF_FLAG_BILATERAL)) ? 1 : 0;
+    const int gi = stage_variant(e, p, flags, small);
     if (p == 0) {
       // the slot is free once the frame that last used it has left the last stage
       SSF_CUDA(e, cudaStreamWaitEvent(st, e->ev_done[s], 0));
@@ -751,11 +795,13 @@ static int prepare_pipeline(EngineImpl* e, uint32_t flags) {
   for (int s = 0; s < P; s++) {
     select_slot(e, s);
     for (int p = 0; p < P; p++) {
-      const int gi = (p == 0 && (flags & SSF_FLAG_BILATERAL)) ? 1 : 0;   // the ingest is always in stage 0
-      if (e->stage_ready[s][p][gi]) continue;
-      int rc = capture_stage(e, s, p, gi);
-      if (rc) { select_slot(e, keep); return rc; }
-      SSF_CUDA(e, cudaGraphUpload(e->stage_graph[s][p][gi], p == 0 ? e->stream : e->stage_stream[p]));
+      for (int small = 0; small < 2; small++) {       // both registration paths: the pick may change from frame to frame
+        const int gi = stage_variant(e, p, flags, small != 0);   // the ingest is always in stage 0
+        if (e->stage_ready[s][p][gi]) continue;
+        int rc = capture_stage(e, s, p, gi);
+        if (rc) { select_slot(e, keep); return rc; }
+        SSF_CUDA(e, cudaGraphUpload(e->stage_graph[s][p][gi], p == 0 ? e->stream : e->stage_stream[p]));
+      }
     }
   }
   select_slot(e, keep);
@@ -768,20 +814,11 @@ int ssf_prepare(SsfHandle h, uint32_t flags) {
   if (rc) return rc;
   // the synchronous frame graph too
   const bool marks = (flags & SSF_FLAG_STAGE_TIMING) != 0;
-  const int gi = ((flags & SSF_FLAG_BILATERAL) ? 1 : 0) | (marks ? 2 : 0);
-  if (e->use_graph && !e->graph_ready[gi]) {
-    if (e->cur_slot != 0) select_slot(e, 0);
-    cudaGraph_t g;
-    const uint64_t before = e->launches;
-    SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    enqueue_frame(e, (gi & 1) != 0, marks);
-    SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
-    e->launches_per_frame[gi] = e->launches - before;
-    e->launches = before;
-    SSF_CUDA(e, cudaGraphInstantiate(&e->graph_exec[gi], g, 0));
-    cudaGraphDestroy(g);
-    e->graph_ready[gi] = true;
-    SSF_CUDA(e, cudaGraphUpload(e->graph_exec[gi], e->stream));
+  if (e->use_graph) {
+    for (int small = 0; small < 2; small++) {
+      rc = ensure_frame_graph(e, ((flags & SSF_FLAG_BILATERAL) ? 1 : 0) | (marks ? 2 : 0) | (small ? 4 : 0), true);
+      if (rc) return rc;
+    }
   }
   for (int p = 1; p < e->nb_stages; p++) SSF_CUDA(e, cudaStreamSynchronize(e->stage_stream[p]));
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -799,12 +836,15 @@ int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const f
   const int P = e->nb_stages;
   if (e->in_flight >= P) { e->err = "every pipeline stage is occupied: ssf_wait_frame first"; return SSF_ERR_STATE; }
   const int s = e->pipe_next;
+  // the model this frame registers against is the last reported one plus at most S insertions per frame
+  // that is still in flight or about to be
+  const bool small = pick_small_icp(e, (long long)e->h_report->counters.nb_visible + (long long)(e->in_flight + 1) * e->S);
   // graphs first (nothing enqueued yet: a failure here leaves the pipeline as it was)
   {
     const int keep = e->cur_slot;
     select_slot(e, s);
     for (int p = 0; p < P; p++) {
-      const int gi = (p == 0 && (flags & SSF_FLAG_BILATERAL)) ? 1 : 0;
+      const int gi = stage_variant(e, p, flags, small);
       if (!e->stage_ready[s][p][gi]) {
         int rc = capture_stage(e, s, p, gi);
         if (rc) { select_slot(e, keep); return rc; }
@@ -812,7 +852,7 @@ int ssf_submit_frame(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const f
     }
   }
   if (e->in_flight == 0) e->pipe_oldest = s;
-  const int rc = submit_enqueue(e, s, rgb, rgb_stride, depth, depth_stride, pose_prior_Rt12, flags);
+  const int rc = submit_enqueue(e, s, rgb, rgb_stride, depth, depth_stride, pose_prior_Rt12, flags, small);
   if (rc) {
     // Part of the frame may be running and its completion event was never recorded: the slot, the
     // shared staging buffers and the prior buffer cannot be reused safely.  Drain everything and
@@ -858,6 +898,14 @@ int ssf_plan_pipeline(const SsfConfig* cfg, int stages, int persistent_segmentat
   const int used = plan_stages_impl(cfg->seg_iter, cfg->icp_iter, persistent_segmentation, stages, first);
   if (nb_steps) *nb_steps = (persistent_segmentation ? 1 : cfg->seg_iter + 2) + 3;
   return used;
+}
+
+int ssf_plan_weights(const SsfConfig* cfg, int persistent_segmentation, int* weights, int capacity) {
+  if (!cfg || !weights) return SSF_ERR_INVALID_ARG;
+  const int G = (persistent_segmentation ? 1 : cfg->seg_iter + 2) + 3;
+  if (capacity < G) return SSF_ERR_INVALID_ARG;
+  for (int g = 0; g < G; g++) weights[g] = step_weight(g, cfg->seg_iter, cfg->icp_iter, persistent_segmentation);
+  return G;
 }
 
 int ssf_get_pipeline_depth(SsfHandle h, int* stages) {

