@@ -455,8 +455,6 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   if (const char* v = getenv("SSF_TPS_PERSISTENT")) e->tps_persistent = (atoi(v) != 0 && e->tps_grid > 0) ? 1 : 0;
   e->icp_debug = 0;
   if (const char* v = getenv("SSF_ICP_DEBUG")) e->icp_debug = atoi(v);
-  e->icp_cache = 0;
-  if (const char* v = getenv("SSF_ICP_CACHE")) e->icp_cache = atoi(v);
   e->icp_loop = 1;
   if (const char* v = getenv("SSF_ICP_LOOP")) e->icp_loop = atoi(v) != 0;   // 0: always the multi-launch registration (A/B)
   e->icp_grid = need_blocks < e->icp_occ * sms ? need_blocks : e->icp_occ * sms;

@@ -163,7 +163,6 @@ struct Engine {
   int icp_occ;           // resident CTAs per SM the system kernel is compiled for
   int icp_stages;        // depth of its TMA-fed shared-memory ring (SSF_ICP_STAGES, default 3)
   int icp_debug;         // profiling knob, see IcpArgs::debug
-  int icp_cache;         // L1 policy of the system kernel's gathers, see IcpArgs::cache (SSF_ICP_CACHE)
   int icp_loop;          // 1 (default): small visible models register in one cluster launch (SSF_ICP_LOOP=0: never)
   // tile-parallel registration over peer memory
   float* xbuf;           // this rank's exchange buffer: [2 parities][SSF_MAX_PEERS][64 floats]
