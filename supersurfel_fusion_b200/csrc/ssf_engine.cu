@@ -167,22 +167,23 @@ static void enqueue_steps(EngineImpl* e, int g0, int g1, bool bilateral, bool pi
 // kernel launches of a step, the quantity that sets a stage's duration at VGA.  Pure function of
 // the configuration (also behind ssf_plan_pipeline for the CPU tests); writes first[0 .. used]
 // and returns the number of stages used.
-// Cost of frame step g in microseconds on a B200 at 640x480 (round-2 measurements, profiles/launches_r2_*.txt:
-// the fused relabelling passes run ~4.5 / ~5.5 us each, four per iteration; the one-launch registration ~3 us
-// per Gauss-Newton iteration).  Only the ratios matter; at other frame sizes they stay roughly the same.
+// Cost of frame step g in microseconds on a B200 at 640x480 (round-2 measurements: SSF_FLAG_STAGE_TIMING gives
+// ingest 13, segmentation 303, extraction 29, registration 49, fusion 47 us per frame; inside the segmentation the
+// fused relabelling passes run ~5 us (colour) / ~6.5 us (colour + disparity) each, four per iteration,
+// profiles/launches_r2_*.txt).  Only the ratios matter; at other frame sizes they stay roughly the same.
 static int step_weight(int g, int seg_iter, int icp_iter, int persistent) {
   const int T = persistent ? 1 : seg_iter + 2, half = seg_iter / 2;
-  if (g == 0) return 8;                                   // ingest
+  if (g == 0) return 13;                                  // ingest
   if (g <= T) {
     const int t = g - 1;
     if (persistent) return 300;
-    if (t < half) return 18;                              // colour-only iteration
-    if (t == half) return 38;                             // RANSAC + inlier moments
-    if (t <= seg_iter) return 22;                         // colour + disparity iteration
-    return 12;                                            // smoothing + render
+    if (t < half) return 20;                              // colour-only iteration
+    if (t == half) return 40;                             // RANSAC + inlier moments
+    if (t <= seg_iter) return 26;                         // colour + disparity iteration
+    return 21;                                            // smoothing + render
   }
-  if (g == T + 1) return 20;                              // extraction
-  return 40 + 3 * icp_iter;                               // registration + fusion
+  if (g == T + 1) return 29;                              // extraction
+  return 66 + 3 * icp_iter;                               // registration + fusion
 }
 
 static int plan_stages_impl(int seg_iter, int icp_iter, int persistent, int stages, int* first) {

@@ -117,6 +117,45 @@ def test_fusion_against_reference_kernels(orc, gold, cfg):
     assert abs(model.confidences[:n].sum() - gold["fused_confidences"][:n].sum()) < 1e-3 * gold["fused_confidences"][:n].sum()
 
 
+def test_stale_removal_against_reference_kernels(orc):
+    """filterModel's age-based removal (`time_diff > delta_t && conf < conf_thresh && stamp > delta_t`,
+    supersurfel_fusion_kernels.cu:429) pinned to the reference's own kernels: the model the reference built over 27
+    frames (delta_t = 20, so the branch can only fire from frame 21 on) and what its model update did to it on frame
+    27 (tests/golden/make_ref_golden_long.py), against the oracle's fusion on the same inputs."""
+    import ast
+    path = os.path.join(os.path.dirname(G), "ref_golden_long_320x240.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/ref_golden_long_320x240.npz has not been generated (needs a GPU)")
+    g = np.load(path)
+    params = dict(ast.literal_eval(str(g["params_json"])))
+    cfg = orc.default_config(cam=tuple(g["cam"][:4]) + (int(g["cam"][4]), int(g["cam"][5])), **params)
+    assert cfg.delta_t == 20 and int(g["stamp"]) > cfg.delta_t
+    nb, nv, stamp = int(g["nb"]), int(g["nv"]), int(g["stamp"])
+    frame = _surfels(orc, g, "frame_")
+    model = orc.Surfels(cfg.nb_supersurfels_max)
+    for name, _, _ in orc.Surfels.FIELDS:
+        getattr(model, name)[:nb] = g["model_" + name][:nb]
+    # which model supersurfels the stale branch must take, straight from its definition
+    age = stamp - g["model_stamps"][:nb, 1]
+    stale = (age > cfg.delta_t) & (g["model_confidences"][:nb] < cfg.conf_thresh) & (g["model_confidences"][:nb] > 0)
+    assert stale.sum() > 0, "the recorded state does not exercise the branch"
+    c = orc.fuse(cfg.cam, frame, model, cfg.nb_supersurfels_max, g["pose_R"], g["pose_t"], g["seg_labels"],
+                 g["seg_slanted"], cfg.range_min, cfg.range_max, stamp, cfg.delta_t, cfg.conf_thresh, nb, nv)
+    want = [int(v) for v in g["fuse_counts"]]
+    # a stale supersurfel inside the visible prefix may still be re-observed (its stamp refreshed) by this very
+    # frame's association before filterModel looks at it, so the branch removes a subset of `stale`
+    assert 0 < c["nb_removed_stale"] <= int(stale.sum())
+    # model size, visible prefix and removals: the reference's (the occlusion test p.z < 0.8 z runs under
+    # --use_fast_math there, so allow the odd borderline supersurfel)
+    assert abs(c["nb_removed"] - want[2]) <= 2 and abs(c["nb_supersurfels"] - want[0]) <= 2, (c, want)
+    assert abs(c["nb_visible"] - want[1]) <= 2, (c, want)
+    # the survivors are the reference's survivors
+    n = min(c["nb_supersurfels"], want[0])
+    d, _ = cKDTree(model.positions[:c["nb_supersurfels"]]).query(g["fused_positions"][:want[0]])
+    assert (d < 1e-5).mean() > 0.97, (d < 1e-5).mean()
+    assert abs(model.confidences[:n].sum() - g["fused_confidences"][:n].sum()) < 2e-2 * g["fused_confidences"][:n].sum()
+
+
 def test_tps_against_reference_kernels(orc, gold, cfg):
     """The reference's label passes race; the oracle is one legal serialisation, so a
     small, seam-localised label mismatch is expected and bounded here.  RNG streams: frame 5 of
