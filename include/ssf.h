@@ -162,7 +162,7 @@ int ssf_get_frame_stats(SsfHandle h, SsfFrameStats* out);
  * returns at once, ssf_wait_frame() blocks until the OLDEST submitted frame is done and returns
  * its stats and pose.  The frame's kernel sequence (ingest -> segmentation iterations -> extraction
  * -> registration + fusion; only the last part touches the model) is cut into
- * ssf_get_pipeline_depth() stages of about equal cost (default 4, SSF_PIPELINE_STAGES=1..6), each
+ * ssf_get_pipeline_depth() stages of about equal cost (default 6, SSF_PIPELINE_STAGES=1..6), each
  * on its own stream, and that many frames may be in flight, one per stage.  Same kernels in the
  * same order per frame: results are identical to ssf_process_frame; latency per frame is
  * unchanged, the frame rate is set by the longest stage.  The input buffers must stay valid until

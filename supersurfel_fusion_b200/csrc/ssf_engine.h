@@ -88,6 +88,8 @@ struct DevicePose { float R[9]; float t[3]; };
 // per pipeline stage, so that consecutive frames can be in different stages (ssf_submit_frame).
 constexpr int SSF_SLOTS = 6;          // upper bound of pipeline stages = frames in flight
 struct FrameSlot {
+  uint8_t* in_rgb;     // staging of the raw inputs: per slot, so that the upload of the next frame (own copy
+  float* in_depth;     // stream) overlaps the first stage of the previous one
   uchar4* rgba;
   float* disp;
   int* labels;
@@ -107,6 +109,7 @@ struct Engine {
   int device;
   cudaStream_t own_stream, stream;
   cudaStream_t stage_stream[SSF_SLOTS];   // pipelined mode: one stream per stage ([0] = `stream`)
+  cudaStream_t copy_stream;               // pipelined mode: input uploads (H2D DMA runs beside the stage kernels)
   FrameSlot slot[SSF_SLOTS];              // slot[0] is what the synchronous entry points use
   int cur_slot;
   int nb_stages;                          // stages = frames in flight of the pipelined mode (SSF_PIPELINE_STAGES)

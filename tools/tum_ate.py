@@ -47,6 +47,10 @@ def main():
     ap.add_argument("--engine", default="oracle", choices=["oracle", "gpu"])
     ap.add_argument("--seq", default=DEFAULT_SEQ)
     ap.add_argument("--frames", type=int, default=10 ** 9)
+    ap.add_argument("--ingest", default="library", choices=["library", "oracle"],
+                    help="gpu engine only: 'library' = 16-bit depth + the CUDA bilateral filter (what a node would call); "
+                         "'oracle' = the oracle's CPU bilateral restatement feeds the CUDA path, i.e. both engines see "
+                         "IDENTICAL inputs and the trajectory difference is the path's alone")
     ap.add_argument("--save-traj", default=None, help="write the per-frame poses (npz: R [n,3,3], t [n,3], valid [n])")
     ap.add_argument("--compare-traj", default=None, help="per-frame deviation from a trajectory saved with --save-traj")
     ap.add_argument("--out", default=None, help="JSON result file (default profiles/tum_fr1_xyz_ate[_gpu].json)")
@@ -72,6 +76,11 @@ def main():
             depth = orc.bilateral_filter(orc.depth16_to_metres(d16, DEPTH_SCALE))
             st = eng.process_frame(rgb, depth)
             R, t = eng.pose()
+        elif args.ingest == "oracle":
+            from oracle import orc
+            st = eng.processFrame(rgb, orc.bilateral_filter(orc.depth16_to_metres(d16, DEPTH_SCALE)))
+            R, t = eng.getPose()
+            gpu_ms += st["gpu_ms"]
         else:
             st = eng.processFrameDepth16(rgb, d16, DEPTH_SCALE, flags=SSF_FLAG_BILATERAL)
             R, t = eng.getPose()
@@ -85,7 +94,9 @@ def main():
     rmse, mean, mx = horn_ate(ts, gt)
     out = {"sequence": "freiburg1_xyz", "frames": len(ts), "icp_valid_frames": int(sum(valid)), "ate_rmse_m": rmse,
            "ate_mean_m": mean, "ate_max_m": mx,
-           "engine": "CPU oracle" if args.engine == "oracle" else "CUDA path (libssf, ssf_process_frame_depth16 + SSF_FLAG_BILATERAL)",
+           "engine": "CPU oracle" if args.engine == "oracle" else
+                     ("CUDA path (libssf, ssf_process_frame_depth16 + SSF_FLAG_BILATERAL)" if args.ingest == "library" else
+                      "CUDA path (libssf, ssf_process_frame) on the oracle's filtered depth: identical inputs to the oracle run"),
            "setup": "TUM launch parameters, in-library bilateral filter, pose prior = previous fused pose (no VO), no MOD",
            "wall_s": time.time() - t_start}
     if args.engine == "gpu":
@@ -103,8 +114,9 @@ def main():
             "frames": n, "max_dt_m": float(dt.max()), "median_dt_m": float(np.median(dt)), "p99_dt_m": float(np.percentile(dt, 99)),
             "max_dR_rad": float(dr.max()), "frames_with_same_icp_validity": same_valid,
             "first_frame_over_1e-4_m": int(np.argmax(dt > 1e-4)) if (dt > 1e-4).any() else None,
-            "note": "per-frame pose of this engine vs the CPU oracle's saved trajectory on the same 790 real frames (the two "
-                    "ingest paths differ: oracle bilateral restatement vs the CUDA bilateral kernel, 2e-6 m on the depth)"}
+            "note": "per-frame pose of this engine vs the CPU oracle's saved trajectory on the same real frames; with --ingest "
+                    "library the two ingest paths differ (oracle bilateral restatement vs the CUDA bilateral kernel, 2e-6 m "
+                    "on the depth, enough to flip label decisions), with --ingest oracle the inputs are identical"}
     ref_path = os.path.join(seq, "estimated.txt")
     if os.path.exists(ref_path):
         ref = {l.split()[0]: [float(v) for v in l.split()[1:4]] for l in open(ref_path) if l.strip() and l[0] != "#"}
@@ -114,6 +126,7 @@ def main():
             out["authors_bundled_trajectory"] = {"frames": len(pairs), "ate_rmse_m": r[0], "ate_mean_m": r[1], "ate_max_m": r[2],
                                                  "note": "full system: ORB VO prior + MOD + YOLO"}
     path = args.out or os.path.join(ROOT, "profiles", "tum_fr1_xyz_ate%s.json" % ("" if args.engine == "oracle" else "_gpu"))
+    out["ingest"] = args.ingest if args.engine == "gpu" else "oracle"
     json.dump(out, open(path, "w"), indent=1)
     print(json.dumps(out))
 
