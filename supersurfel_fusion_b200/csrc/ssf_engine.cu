@@ -481,7 +481,7 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
     A(dalloc(&r, (size_t)S * nbs * tps_rng_state_bytes()));
     e->rng = r;
   }
-  A(dalloc(&e->filt_a, (size_t)S * 8)); A(dalloc(&e->filt_b, (size_t)S * 8));
+  A(dalloc(&e->filt_a, (size_t)S * 16)); A(dalloc(&e->filt_b, (size_t)S * 8));   // filt_a also serves as the 11-plane scratch of tps_filter_kernel<false>
   A(dalloc(&e->xsums, (size_t)S * 16));
   A(dalloc(&e->tps_barrier, (size_t)32));
   if (getenv("SSF_TPS_TRACE") && e->tps_grid > 0) {

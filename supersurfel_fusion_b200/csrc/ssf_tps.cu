@@ -948,25 +948,98 @@ __device__ __forceinline__ void tps_filter_finish_item(const TpsArgs& a, const f
   s.theta_b.z = X0 - s.xy_rg.x * X1 - s.xy_rg.y * X2;
 }
 
-// single-CTA version (multi-kernel path).  SMEM: both Jacobi buffers live in shared memory (64 bytes per
-// node: up to 3584 superpixels, i.e. 1280x960 at the default cell size is one step beyond; larger frames
-// run the same code on the global buffers).  An iteration then costs a shared-memory round trip instead
-// of an L2 round trip per neighbour, and the fused final merge has all its loads in flight at once.
+// single-CTA version (multi-kernel path): the node state as planes -- the two Jacobi copies of X (3 floats
+// each), the anchor Z (3) and the centroid (2): 44 bytes per node.  SMEM: the planes live in shared memory
+// (up to 5200 superpixels: 640x480 and 1280x960 at the default cell size; larger frames run the same code
+// on a global scratch buffer).  An iteration then costs a shared-memory round trip instead of an L2 round
+// trip per neighbour, and the fused final merge has all its loads in flight at once.
+struct FilterPlanes {
+  float* xa;    // [3][S] current X
+  float* xb;    // [3][S] next X
+  float* z;     // [3][S] anchor
+  float* p;     // [2][S] centroid
+  int S;
+};
+constexpr int kFilterFloatsPerNode = 11;
+
+__device__ __forceinline__ void tps_filter_iter_planes(const TpsArgs& a, const FilterPlanes& f, const float* cur,
+                                                       float* nxt, int idx, float alpha, float beta, float threshold) {
+  const int vv[4] = {-1, 0, 0, 1};
+  const int uu[4] = {0, -1, 1, 0};
+  const int S = f.S;
+  const int x = idx % a.gx, y = idx / a.gx;
+  const V3 Xi = v3(cur[idx], cur[S + idx], cur[2 * S + idx]);
+  const V3 Zi = v3(f.z[idx], f.z[S + idx], f.z[2 * S + idx]);
+  const float pxi = f.p[idx], pyi = f.p[S + idx];
+  Sym3 A = sym3(alpha, 0.f, 0.f, alpha, 0.f, alpha);
+  V3 R = alpha * Zi;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int yy = y + vv[j], xx = x + uu[j];
+    if (yy >= 0 && yy < a.gy && xx >= 0 && x < a.gx) {   // sic: x, not xx (reference :582-583)
+      const int nidx = yy * a.gx + xx;
+      if (nidx >= a.S) continue;
+      const V3 Xj = v3(cur[nidx], cur[S + nidx], cur[2 * S + nidx]);
+      const float dx = pxi - f.p[nidx];
+      const float dy = pyi - f.p[S + nidx];
+      const float dz = Xi.x - Xj.x;
+      if (isfinite(dz) && dz * dz < threshold * threshold) {
+        A.xx += beta * 2.f;
+        A.xy += -beta * dx;
+        A.xz += -beta * dy;
+        A.yy += beta * (2.f + dx * dx);
+        A.yz += beta * (dx * dy);
+        A.zz += beta * (2.f + dy * dy);
+        R.x += beta * (2.f * Xj.x + dx * Xj.y + dy * Xj.z);
+        R.y += beta * (-dx * Xj.x + 2.f * Xj.y);
+        R.z += beta * (-dy * Xj.x + 2.f * Xj.z);
+      }
+    }
+  }
+  Sym3 Ai;
+  V3 Xn = Xi;
+  if (invert(A, Ai)) Xn = Ai * R;
+  nxt[idx] = Xn.x; nxt[S + idx] = Xn.y; nxt[2 * S + idx] = Xn.z;
+}
+
 template <bool SMEM>
-__global__ void __launch_bounds__(1024) tps_filter_kernel(TpsArgs a, float* bufA, float* bufB, int iters, float alpha,
-                                                          float beta, float threshold, int merge) {
+__global__ void __launch_bounds__(1024) tps_filter_kernel(TpsArgs a, float* scratch, int iters, float alpha, float beta,
+                                                          float threshold, int merge) {
   pdl_sync();
   extern __shared__ float filt_smem[];
-  float* cur = SMEM ? filt_smem : bufA;
-  float* nxt = SMEM ? filt_smem + 8 * (size_t)a.S : bufB;
-  for (int i = threadIdx.x; i < a.S; i += blockDim.x) tps_filter_init_item(a, cur, i, merge != 0);
+  float* base = SMEM ? filt_smem : scratch;
+  const int S = a.S;
+  FilterPlanes f = {base, base + 3 * (size_t)S, base + 6 * (size_t)S, base + 9 * (size_t)S, S};
+  // init (TPS_RGBD_kernels.cu:510-540), with the last merge of the fused passes folded in
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    Superpixel s;
+    if (merge) {
+      s = tps_superpixel_from_sums<true>(a.sums[i]);
+      a.sp[i] = s;
+    } else {
+      s = a.sp[i];
+    }
+    const float X0 = s.xy_rg.x * s.theta_b.x + s.xy_rg.y * s.theta_b.y + s.theta_b.z;
+    f.xa[i] = X0; f.xa[S + i] = s.theta_b.x; f.xa[2 * S + i] = s.theta_b.y;
+    f.z[i] = X0; f.z[S + i] = s.theta_b.x; f.z[2 * S + i] = s.theta_b.y;
+    f.p[i] = s.xy_rg.x; f.p[S + i] = s.xy_rg.y;
+  }
   __syncthreads();
+  float* cur = f.xa;
+  float* nxt = f.xb;
   for (int it = 0; it < iters; it++) {
-    for (int idx = threadIdx.x; idx < a.S; idx += blockDim.x) tps_filter_iter_item(a, cur, nxt, idx, alpha, beta, threshold);
+    for (int idx = threadIdx.x; idx < S; idx += blockDim.x) tps_filter_iter_planes(a, f, cur, nxt, idx, alpha, beta, threshold);
     __syncthreads();
     float* t = cur; cur = nxt; nxt = t;
   }
-  for (int i = threadIdx.x; i < a.S; i += blockDim.x) tps_filter_finish_item(a, cur, i);
+  // finish (TPS_RGBD_kernels.cu:596-614)
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    Superpixel& s = a.sp[i];
+    const float X0 = cur[i], X1 = cur[S + i], X2 = cur[2 * S + i];
+    s.theta_b.x = X1;
+    s.theta_b.y = X2;
+    s.theta_b.z = X0 - f.p[i] * X1 - f.p[S + i] * X2;
+  }
 }
 
 // ---- slanted-plane depth render (TPS_RGBD_kernels.cu:469-508) -> interleaved map -----
@@ -1314,12 +1387,12 @@ void launch_tps(Engine* e, int first, int last) {
     } else if (step <= nbIters) {            // colour + disparity iteration
       launch_iteration<true>(e, a, done);
     } else {                                 // plane smoothing + slanted-depth render
-      const size_t filt_bytes = (size_t)e->S * 16 * sizeof(float);
+      const size_t filt_bytes = (size_t)e->S * kFilterFloatsPerNode * sizeof(float);
       if (filt_bytes <= kFilterSmemMax)
-        launch_pdl(e, tps_filter_kernel<true>, dim3(1), dim3(1024), filt_bytes, a, e->filt_a, e->filt_b, e->cfg.filter_iter,
+        launch_pdl(e, tps_filter_kernel<true>, dim3(1), dim3(1024), filt_bytes, a, e->filt_a, e->cfg.filter_iter,
                    e->cfg.filter_alpha, e->cfg.filter_beta, e->cfg.filter_threshold, fused ? 1 : 0);
-      else
-        launch_pdl(e, tps_filter_kernel<false>, dim3(1), dim3(1024), 0, a, e->filt_a, e->filt_b, e->cfg.filter_iter,
+      else   // filt_a holds 16 floats per node: room for the 11 planes
+        launch_pdl(e, tps_filter_kernel<false>, dim3(1), dim3(1024), 0, a, e->filt_a, e->cfg.filter_iter,
                    e->cfg.filter_alpha, e->cfg.filter_beta, e->cfg.filter_threshold, fused ? 1 : 0);
       launch_pdl(e, tps_render_kernel, dim3(grd), dim3(blk), 0, a, e->lmap);
       e->launches += 2;
