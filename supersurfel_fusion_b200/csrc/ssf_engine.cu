@@ -20,6 +20,7 @@ namespace ssf {
 
 void launch_icp_set_transform(Engine* e, const float* R, const float* t);
 size_t tps_rng_state_bytes();
+bool tps_make_label_map(void* map128, const int* labels, int W, int H);
 void tps_configure();
 size_t tps_trace_bytes(int grid);
 int tps_persistent_grid(int device, int gx, int gy, int cell, int height, int nb_iters, int* cache_slots);
@@ -511,6 +512,13 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
     f.frame.stride = e->frame.stride;
     A(dalloc(&f.lmap, N)); A(dalloc(&f.frame.base, (size_t)P_COUNT * e->frame.stride));
     A(dalloc(&f.ftab, (size_t)2 * S)); A(dalloc(&f.matched, (size_t)S)); A(dalloc(&f.best, (size_t)S));
+  }
+  if (err == cudaSuccess) {
+    // tensor maps of the label images (fused pass, TMA staging); any failure falls back to plain loads
+    e->tps_tma = 1;
+    if (const char* v = getenv("SSF_TPS_TMA")) e->tps_tma = atoi(v) != 0;
+    for (int k = 0; k < SSF_SLOTS && e->tps_tma; k++)
+      if (!tps_make_label_map(e->label_map[k], e->slot[k].labels, e->W, e->H)) e->tps_tma = 0;
   }
   for (int p = 1; p < SSF_SLOTS; p++) A(cudaStreamCreateWithFlags(&e->stage_stream[p], cudaStreamNonBlocking));
   A(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));

@@ -27,6 +27,7 @@
 #include "ssf_math.cuh"
 
 #include <cooperative_groups.h>
+#include <cuda.h>            // CUtensorMap (types only; the encoder is resolved at run time)
 #include <curand_kernel.h>
 
 namespace cg = cooperative_groups;
@@ -493,10 +494,16 @@ __device__ __forceinline__ int div_magic(int a, unsigned long long magic) {
   return (int)(((unsigned long long)(unsigned)a * magic) >> 32);
 }
 
-template <bool DISP>
-__global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, int OX, int OY) {
+// TMA: the label rows of the tile arrive as ONE 2-D tensor-map copy (cp.async.bulk.tensor, box 64 x 17
+// int32) issued by one thread and counted on an mbarrier, instead of three 8-byte loads + stores per
+// thread; out-of-image texels come back as 0 and are patched to -1 by the (border) tiles that have any.
+// Needs a 16-byte row pitch (W % 4 == 0), otherwise the loads below do the same job.
+template <bool DISP, bool TMA>
+__global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, int OX, int OY,
+                                                                     const __grid_constant__ CUtensorMap label_map) {
   pdl_sync();
-  __shared__ int lab[TILE_LROWS][TILE_COLS];
+  __shared__ __align__(128) int lab[TILE_LROWS][TILE_COLS];
+  __shared__ __align__(8) uint64_t lab_bar;
   __shared__ Superpixel win[TILE_WIN];
   const int tid = threadIdx.x;
   const int lane = tid & 31, wrp = tid >> 5;
@@ -511,6 +518,20 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
   const int xs0 = 4 * q0 + (OX ? 0 : -2);                // first image column of the staged labels
   const int ry0 = blockIdx.y * TILE_ROWS;
   const int y0 = 2 * ry0 + OY;                           // first active row; staged rows start at y0 - 1
+
+  if (TMA) {
+    if (tid == 0) {
+      mbar_init(&lab_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&lab_bar, TILE_LROWS * TILE_COLS * (int)sizeof(int));
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+              smem_u32(&lab[0][0])),
+          "l"(&label_map), "r"(xs0), "r"(y0 - 1), "r"(smem_u32(&lab_bar))
+          : "memory");
+    }
+  }
 
   // ---- window of superpixels whose means this tile may need: the grid cells under the tile plus a
   // margin of one cell (boundaries drift a few pixels over the 4 * seg_iter passes); with small
@@ -569,7 +590,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
     const int yy = y0 - 1 + r;
     const int xx = xs0 + 2 * lane;
     int2 v = make_int2(-1, -1);
-    if (r < TILE_LROWS && yy >= 0 && yy < a.H) {
+    if (!TMA && r < TILE_LROWS && yy >= 0 && yy < a.H) {
       const size_t row = (size_t)yy * a.W;
       if (xx >= 0 && xx + 1 < a.W && (((row + xx) & 1) == 0)) {
         v = *reinterpret_cast<const int2*>(a.labels + row + xx);
@@ -618,10 +639,29 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
     Superpixel& s = win[slot];
     s.theta_b.x = tx; s.theta_b.y = ty; s.theta_b.z = tz;
   }
+  if (TMA) {
+    __syncthreads();                       // the barrier was initialised by thread 0: nobody polls it before this
+    mbar_wait(&lab_bar, 0);
+    // the tensor map fills texels outside the image with 0, a valid label: patch them (border tiles only)
+    const bool inside = xs0 >= 0 && xs0 + TILE_COLS <= a.W && y0 - 1 >= 0 && y0 - 1 + TILE_LROWS <= a.H;
+    if (!inside) {
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const int r = wrp + k * TILE_ROWS;
-    if (r < TILE_LROWS) *reinterpret_cast<int2*>(&lab[r][2 * lane]) = lv[k];
+      for (int k = 0; k < 3; k++) {
+        const int r = wrp + k * TILE_ROWS;
+        const int yy = y0 - 1 + r, xx = xs0 + 2 * lane;
+        if (r < TILE_LROWS) {
+          const bool row_out = yy < 0 || yy >= a.H;
+          if (row_out || xx < 0 || xx >= a.W) lab[r][2 * lane] = -1;
+          if (row_out || xx + 1 < 0 || xx + 1 >= a.W) lab[r][2 * lane + 1] = -1;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int r = wrp + k * TILE_ROWS;
+      if (r < TILE_LROWS) *reinterpret_cast<int2*>(&lab[r][2 * lane]) = lv[k];
+    }
   }
   __syncthreads();
 
@@ -1250,6 +1290,33 @@ void tps_configure() {
   cudaFuncSetAttribute(tps_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFilterSmemMax);
 }
 
+// The 2-D tensor map over a slot's label image (int32, H rows of W) with the tile box of the fused pass;
+// cuTensorMapEncodeTiled is resolved through the runtime (no link-time dependency on libcuda).  Returns
+// false when the image cannot be described (row pitch not a multiple of 16 bytes) or the driver lacks it.
+bool tps_make_label_map(void* map128, const int* labels, int W, int H) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+  if (W % 4 != 0) return false;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+      q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
+  const cuuint64_t strides[1] = {(cuuint64_t)W * sizeof(int)};
+  const cuuint32_t box[2] = {(cuuint32_t)TILE_COLS, (cuuint32_t)TILE_LROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = reinterpret_cast<EncodeFn>(fn)(reinterpret_cast<CUtensorMap*>(map128), CU_TENSOR_MAP_DATA_TYPE_INT32, 2,
+                                                     const_cast<int*>(labels), dims, strides, box, estr,
+                                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS;
+}
+
 void tps_init_rng(Engine* e) {
   const int n = e->S * e->cfg.nb_samples;
   launch_pdl(e, tps_rng_init_kernel, dim3(cdiv(n, 128)), dim3(128), 0, reinterpret_cast<curandState*>(e->rng), n);
@@ -1311,7 +1378,9 @@ static void launch_pass_fused(Engine* e, TpsArgs a, int p, int OX, int OY) {
   a.sums_nxt = sums_buffer(e, p + 1);
   a.sums_zero = sums_buffer(e, p + 2);
   dim3 grd(cdiv(pairs, TILE_LANES / 2), cdiv(a.raw_h, TILE_ROWS));
-  launch_pdl(e, tps_pass_tile_kernel<DISP>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY);
+  const CUtensorMap& map = *reinterpret_cast<const CUtensorMap*>(e->label_map[e->cur_slot]);
+  if (e->tps_tma) launch_pdl(e, tps_pass_tile_kernel<DISP, true>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+  else launch_pdl(e, tps_pass_tile_kernel<DISP, false>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
   e->launches += 1;
 }
 
