@@ -337,6 +337,32 @@ def icp_roofline(device, peaks):
            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
            "n_src": n, "us_per_launch": ms * 1e3, "algorithmic_bytes_per_src": ICP_BYTES_PER_SRC,
            "streamed_only_gbs": n * 36 / (ms * 1e-3) / 1e9, "inlier_frac": float(sys29[28]) / n}
+    # the same sources binned by the 32x32-pixel tile they project to (what a model prefix kept in image order
+    # looks like): the two gathers of neighbouring lanes then share sectors / L1 lines, and the kernel is back on
+    # the HBM streams.  The scattered figure above stays the headline (SURVEY.md section 8d sizing).
+    try:
+        cam = prob["cam"]
+        uu = np.clip(prob["src_pos"][:, 0] / prob["src_pos"][:, 2] * cam[0] + cam[2], 0, cam[5] - 1).astype(np.int32) >> 5
+        vv = np.clip(prob["src_pos"][:, 1] / prob["src_pos"][:, 2] * cam[1] + cam[3], 0, cam[4] - 1).astype(np.int32) >> 5
+        order = np.argsort(vv * ((cam[5] + 31) >> 5) + uu, kind="stable")
+        bp, bc, bo = (np.ascontiguousarray(prob[k][order]) for k in ("src_pos", "src_col", "src_ori"))
+        eng.setModelPointers(SsfSurfels(_ptr(bp), _ptr(bc), None, _ptr(bo), None, None, None), n, n)
+        sys_b = eng.icpSystem(R, t, n)
+        for _ in range(3):
+            eng.icpSystemEnqueue(R, t, n, 1)
+        eng.synchronize()
+        eng.timerStart()
+        eng.icpSystemEnqueue(R, t, n, L)
+        ms_b = eng.timerStop() / L
+        out["binned_by_tile"] = {"us_per_launch": ms_b * 1e3, "achieved": n * ICP_BYTES_PER_SRC / (ms_b * 1e-3) / 1e9,
+                                 "frac": n * ICP_BYTES_PER_SRC / (ms_b * 1e-3) / 1e9 / peak,
+                                 "streamed_only_gbs": n * 36 / (ms_b * 1e-3) / 1e9,
+                                 "streamed_only_frac": n * 36 / (ms_b * 1e-3) / 1e9 / peak,
+                                 "inliers_equal_scattered": bool(sys_b[28] == sys29[28]),
+                                 "what": "same 16 Mi sources sorted by projected 32x32-pixel tile: gathers hit L1"}
+        del bp, bc, bo
+    except Exception as exc:
+        out["binned_by_tile"] = {"unavailable": repr(exc)[:200]}
     # latency at realistic sizes (L2 resident, launch bound): microseconds per system build
     lat = {}
     for m in (1200, 5000, 50000, 100000):

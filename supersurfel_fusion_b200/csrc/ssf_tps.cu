@@ -468,6 +468,7 @@ constexpr int TILE_ROWS = 8;                   // active rows per tile (16 image
 constexpr int TILE_THREADS = TILE_LANES * TILE_ROWS;
 constexpr int TILE_COLS = 2 * TILE_LANES;      // image columns of a tile
 constexpr int TILE_LROWS = 2 * TILE_ROWS + 1;  // label rows staged: y0 - 1 .. y0 + 2 * TILE_ROWS - 1
+constexpr int TILE_SCOLS = TILE_COLS + 4;      // staged columns: a TMA box must start on a 16-byte boundary (x % 4 == 0)
 constexpr int TILE_WIN = 64;                   // capacity of the means window (superpixels)
 
 struct SpWindow {
@@ -494,15 +495,18 @@ __device__ __forceinline__ int div_magic(int a, unsigned long long magic) {
   return (int)(((unsigned long long)(unsigned)a * magic) >> 32);
 }
 
-// TMA: the label rows of the tile arrive as ONE 2-D tensor-map copy (cp.async.bulk.tensor, box 64 x 17
+// TMA: the label rows of the tile arrive as ONE 2-D tensor-map copy (cp.async.bulk.tensor, box 68 x 17
 // int32) issued by one thread and counted on an mbarrier, instead of three 8-byte loads + stores per
 // thread; out-of-image texels come back as 0 and are patched to -1 by the (border) tiles that have any.
-// Needs a 16-byte row pitch (W % 4 == 0), otherwise the loads below do the same job.
+// The innermost box coordinate must be 16-byte aligned (measured: x = -2 raises an illegal-instruction
+// fault), so the box starts at the multiple of four at or below the tile's first column (the tile starts at
+// 4 q0 - 2 in the OX = 0 passes) and is four columns wider than the tile; `co` is where the tile begins
+// inside the staged rows.  Needs a 16-byte row pitch (W % 4 == 0), otherwise the loads below do the job.
 template <bool DISP, bool TMA>
 __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, int OX, int OY,
                                                                      const __grid_constant__ CUtensorMap label_map) {
   pdl_sync();
-  __shared__ __align__(128) int lab[TILE_LROWS][TILE_COLS];
+  __shared__ __align__(128) int lab[TILE_LROWS][TILE_SCOLS];
   __shared__ __align__(8) uint64_t lab_bar;
   __shared__ Superpixel win[TILE_WIN];
   const int tid = threadIdx.x;
@@ -518,17 +522,18 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
   const int xs0 = 4 * q0 + (OX ? 0 : -2);                // first image column of the staged labels
   const int ry0 = blockIdx.y * TILE_ROWS;
   const int y0 = 2 * ry0 + OY;                           // first active row; staged rows start at y0 - 1
+  const int co = OX ? 0 : 2;                             // column of the staged rows that holds image column xs0
 
   if (TMA) {
     if (tid == 0) {
       mbar_init(&lab_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&lab_bar, TILE_LROWS * TILE_COLS * (int)sizeof(int));
+      mbar_expect_tx(&lab_bar, TILE_LROWS * TILE_SCOLS * (int)sizeof(int));
       asm volatile(
           "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
               smem_u32(&lab[0][0])),
-          "l"(&label_map), "r"(xs0), "r"(y0 - 1), "r"(smem_u32(&lab_bar))
+          "l"(&label_map), "r"(xs0 - co), "r"(y0 - 1), "r"(smem_u32(&lab_bar))
           : "memory");
     }
   }
@@ -651,8 +656,8 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
         const int yy = y0 - 1 + r, xx = xs0 + 2 * lane;
         if (r < TILE_LROWS) {
           const bool row_out = yy < 0 || yy >= a.H;
-          if (row_out || xx < 0 || xx >= a.W) lab[r][2 * lane] = -1;
-          if (row_out || xx + 1 < 0 || xx + 1 >= a.W) lab[r][2 * lane + 1] = -1;
+          if (row_out || xx < 0 || xx >= a.W) lab[r][co + 2 * lane] = -1;
+          if (row_out || xx + 1 < 0 || xx + 1 >= a.W) lab[r][co + 2 * lane + 1] = -1;
         }
       }
     }
@@ -660,7 +665,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       const int r = wrp + k * TILE_ROWS;
-      if (r < TILE_LROWS) *reinterpret_cast<int2*>(&lab[r][2 * lane]) = lv[k];
+      if (r < TILE_LROWS) *reinterpret_cast<int2*>(&lab[r][co + 2 * lane]) = lv[k];
     }
   }
   __syncthreads();
@@ -676,7 +681,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
-      for (int k = 0; k < 3; k++) L[r][k] = lab[2 * wrp + r][c - 1 + k];
+      for (int k = 0; k < 3; k++) L[r][k] = lab[2 * wrp + r][co + c - 1 + k];
     L[0][3] = L[1][3] = L[2][3] = -1;
     const SpTile<DISP> src = {w};
     tps_decide<DISP>(a, src, pin, x, y, L, 1, d, dv);
@@ -1308,7 +1313,7 @@ bool tps_make_label_map(void* map128, const int* labels, int W, int H) {
   }
   const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
   const cuuint64_t strides[1] = {(cuuint64_t)W * sizeof(int)};
-  const cuuint32_t box[2] = {(cuuint32_t)TILE_COLS, (cuuint32_t)TILE_LROWS};
+  const cuuint32_t box[2] = {(cuuint32_t)TILE_SCOLS, (cuuint32_t)TILE_LROWS};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult rc = reinterpret_cast<EncodeFn>(fn)(reinterpret_cast<CUtensorMap*>(map128), CU_TENSOR_MAP_DATA_TYPE_INT32, 2,
                                                      const_cast<int*>(labels), dims, strides, box, estr,
