@@ -25,26 +25,10 @@ void tps_configure();
 size_t tps_trace_bytes(int grid);
 int tps_persistent_grid(int device, int gx, int gy, int cell, int height, int nb_iters, int* cache_slots);
 
-struct FrameReport {
-  Counters counters;
-  DevicePose pose;
-  int icp_active, icp_valid, icp_iters;
-  float icp_inliers;
-  double icp_error;
-};
-
 __global__ void frame_end_kernel(Counters* counters, const DevicePose* pose, const IcpState* icp, FrameReport* rep,
                                  int advance) {
   pdl_sync();
-  rep->counters = *counters;
-  rep->pose = *pose;
-  rep->icp_active = icp->active;
-  rep->icp_valid = icp->active ? icp->valid : 0;
-  rep->icp_iters = icp->active ? icp->iter : 0;
-  rep->icp_inliers = icp->active ? icp->inliers : 0.0f;
-  rep->icp_error = icp->active ? icp->error : 0.0;
-  if (advance & 1) counters->stamp += 1;                  // supersurfel_fusion.cu:521
-  if (advance & 2) counters->seg_stamp = counters->stamp; // synchronous mode: the two stamps move together
+  frame_report(counters, pose, icp, rep, advance);
 }
 
 // end of the segmentation stage of the pipelined mode: the next frame to be segmented is stamp + 1
@@ -239,9 +223,7 @@ static void enqueue_track(EngineImpl* e, FrameReport* report, int advance, bool 
     stage_mark(e, marks, 4);
   }
   StageRange r(e, "ssf:fusion");
-  launch_fuse(e);
-  launch_pdl(e, frame_end_kernel, dim3(1), dim3(1), 0, e->counters, e->pose, e->icp, report, advance);
-  e->launches++;
+  launch_fuse(e, report, advance);          // the last kernel of the update also writes the frame's report
   stage_mark(e, marks, 5);
 }
 

@@ -83,6 +83,30 @@ struct Counters {
 
 struct DevicePose { float R[9]; float t[3]; };
 
+// what a frame hands back to the host (one small D2H copy per frame)
+struct FrameReport {
+  Counters counters;
+  DevicePose pose;
+  int icp_active, icp_valid, icp_iters;
+  float icp_inliers;
+  double icp_error;
+};
+
+
+// The frame's report + stamp bookkeeping (supersurfel_fusion.cu:521), one thread.
+__device__ __forceinline__ void frame_report(Counters* counters, const DevicePose* pose, const IcpState* icp, FrameReport* rep,
+                                             int advance) {
+  rep->counters = *counters;
+  rep->pose = *pose;
+  rep->icp_active = icp->active;
+  rep->icp_valid = icp->active ? icp->valid : 0;
+  rep->icp_iters = icp->active ? icp->iter : 0;
+  rep->icp_inliers = icp->active ? icp->inliers : 0.0f;
+  rep->icp_error = icp->active ? icp->error : 0.0;
+  if (advance & 1) counters->stamp += 1;                  // supersurfel_fusion.cu:521
+  if (advance & 2) counters->seg_stamp = counters->stamp; // synchronous mode: the two stamps move together
+}
+
 // Everything that belongs to ONE frame on its way through the stages: the segmentation images and
 // per-superpixel state, and what segmentation + extraction hand to registration + fusion.  One set
 // per pipeline stage, so that consecutive frames can be in different stages (ssf_submit_frame).
@@ -240,7 +264,9 @@ void launch_ingest(Engine* e, const uint8_t* rgb_dev, size_t rgb_stride, const f
 int tps_step_count(const Engine* e);
 void launch_tps(Engine* e, int first = 0, int last = -1);   // segmentation steps [first, last)
 void launch_extract(Engine* e);
-void launch_fuse(Engine* e);
+// model update; with `report` the frame's report is written (and the stamps advanced, see frame_report) by the
+// last kernel of the update instead of by a launch of its own
+void launch_fuse(Engine* e, FrameReport* report = nullptr, int advance = 0);
 void launch_build_lmap(Engine* e, const float* slanted_dev);
 void launch_frame_tables(Engine* e);
 void launch_model_lab(Engine* e, int n);

@@ -190,10 +190,15 @@ __global__ void invalidate_kernel(SurfelSet frame, float4* ftab, const uint8_t* 
 // findBestMatches (supersurfel_fusion_kernels.cu:522-599)
 __global__ void associate_kernel(SurfelSet model, SurfelSet frame, const float4* __restrict__ ftab,
                                  const int2* __restrict__ lmap, unsigned char* matched, unsigned long long* best,
-                                 const DevicePose* pose, const Counters* counters, CamK cam, float z_min,
+                                 const DevicePose* pose, Counters* counters, CamK cam, float z_min,
                                  float z_max) {
   pdl_sync();
   const int n = counters->nb_supersurfels > 0 ? counters->nb_visible : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {     // per-frame counters of the update start at zero
+    counters->nb_matched = 0;
+    counters->nb_inserted = 0;
+    counters->nb_removed = 0;
+  }
   const M3 R = pose_R(pose);
   const V3 t = pose_t(pose);
   const M3 Rview = transpose(R);
@@ -531,9 +536,11 @@ __global__ void __launch_bounds__(PART_THREADS) partition_scatter_kernel(SurfelS
   }
 }
 
-__global__ void partition_copyback_kernel(SurfelSet src, SurfelSet dst, const Counters* counters,
-                                          const int* skip_filter) {
+__global__ void partition_copyback_kernel(SurfelSet src, SurfelSet dst, Counters* counters, const int* skip_filter,
+                                          const DevicePose* pose, const IcpState* icp, FrameReport* report, int advance) {
   pdl_sync();
+  // the counters are final since partition_scan_kernel: the frame's report rides on this launch
+  if (report && blockIdx.x == 0 && threadIdx.x == 0) frame_report(counters, pose, icp, report, advance);
   if (*skip_filter) return;
   const int n = counters->pad;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -543,13 +550,6 @@ __global__ void partition_copyback_kernel(SurfelSet src, SurfelSet dst, const Co
   for (int p = 0; p < P_COUNT; p++) row[p] = src.plane(p)[i];
 #pragma unroll
   for (int p = 0; p < P_COUNT; p++) dst.plane(p)[i] = row[p];
-}
-
-__global__ void fuse_begin_kernel(Counters* counters) {
-  pdl_sync();
-  counters->nb_matched = 0;
-  counters->nb_inserted = 0;
-  counters->nb_removed = 0;
 }
 
 // ------------------------------------------------------- layout conversion etc.
@@ -781,12 +781,11 @@ void launch_invalidate(Engine* e, const uint8_t* mask_dev) {
   e->launches++;
 }
 
-void launch_fuse(Engine* e) {
+void launch_fuse(Engine* e, FrameReport* report, int advance) {
   const CamK cam = cam_of(e);
   int* skip = e->scan_tmp;            // [0] skip flag, block histograms from [4]
   int* hist = e->scan_tmp + 4;
   const int cap_blocks = cdiv(e->cap, PART_CHUNK);
-  launch_pdl(e, fuse_begin_kernel, dim3(1), dim3(1), 0, e->counters);
   launch_pdl(e, associate_kernel, dim3(cdiv(e->cap, 256) < 1184 ? cdiv(e->cap, 256) : 1184), dim3(256), 0, 
       e->model, e->frame, e->ftab, e->lmap, e->matched, e->best, e->pose, e->counters, cam, e->cfg.range_min,
       e->cfg.range_max);
@@ -800,8 +799,9 @@ void launch_fuse(Engine* e) {
   launch_pdl(e, partition_scan_kernel, dim3(1), dim3(1024), 0, hist, e->counters, skip);
   launch_pdl(e, partition_scatter_kernel, dim3(cap_blocks), dim3(PART_THREADS), 0, e->model, e->model_alt, e->states, hist,
                                                                        e->counters, skip);
-  launch_pdl(e, partition_copyback_kernel, dim3(cdiv(e->cap, 256)), dim3(256), 0, e->model_alt, e->model, e->counters, skip);
-  e->launches += 8;
+  launch_pdl(e, partition_copyback_kernel, dim3(cdiv(e->cap, 256)), dim3(256), 0, e->model_alt, e->model, e->counters, skip,
+             e->pose, e->icp, report, advance);
+  e->launches += 7;
 }
 
 static Members members_of(const SsfSurfels& s) {

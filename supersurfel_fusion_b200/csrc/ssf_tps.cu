@@ -791,20 +791,24 @@ __device__ __forceinline__ void tps_init_sample_item(const TpsArgs& a, float4* s
     y = (float)((double)cy + ((double)radius * 2.) * (double)(curand_uniform(&rnd) - 1.f));
     i = tex_label(a, x, y);
   }
-  const float dxs[4] = {-1.f, 0.f, 1.f, 0.f};
-  const float dys[4] = {0.f, -1.f, 0.f, 1.f};
   float3 xyd[3];
+  // The walk re-reads the label under the CURRENT position at every step (TPS_RGBD_kernels.cu:360); labels do
+  // not change during this kernel, so that read is carried along and refreshed only when the walker moves --
+  // together with the disparity of the new position, one round of loads per move instead of two in series.
+  int here = i;                        // label under (x, y)
   const float d0 = tex_disp(a, x, y);
   xyd[0] = xyd[1] = xyd[2] = make_float3(x, y, d0);
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     for (int w = 0; w < nbWalks; w++) {
-      const int dir = curand(&rnd) & 3;
-      const float next_x = x + dxs[dir], next_y = y + dys[dir];
-      i = tex_label(a, x, y);
-      if (i == index && next_x >= 0 && next_x < (float)a.W && next_y >= 0 && next_y < (float)a.H) {
+      const int dir = curand(&rnd) & 3;                       // 0 left, 1 up, 2 right, 3 down
+      const float next_x = x + ((dir & 1) ? 0.f : (float)(dir - 1));
+      const float next_y = y + ((dir & 1) ? (float)(dir - 2) : 0.f);
+      if (here == index && next_x >= 0 && next_x < (float)a.W && next_y >= 0 && next_y < (float)a.H) {
         x = next_x; y = next_y;
-        const float dd = tex_disp(a, x, y);
+        const size_t at = (size_t)tex_coord(y, a.H) * a.W + tex_coord(x, a.W);
+        here = a.labels[at];
+        const float dd = a.disp[at];
         if (isfinite(dd)) xyd[j] = make_float3(x, y, dd);
       }
     }
