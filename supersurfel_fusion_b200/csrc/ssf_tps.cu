@@ -670,90 +670,22 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
   }
   __syncthreads();
 
-  // ---- decide on the pass-start state.  Only pixels on a superpixel boundary (about a third of the active ones,
-  // strung along lines, so nearly every warp holds a few) can change label and need the energy evaluation
-  // against up to four neighbours -- ~45 % of the kernel's instructions when every warp runs it for its few
-  // boundary lanes.  The tile therefore compacts them: every thread settles the cheap part for its own pixel
-  // and queues the pixel if it is a candidate; the queue is then evaluated by as many threads as it has entries
-  // (full warps), and the decisions come back through shared memory for the apply phase, which needs the
-  // original lane order (pair partners are neighbouring lanes).
-  __shared__ int cand_count[TILE_ROWS];
-  __shared__ unsigned char cand_list[TILE_THREADS];
-  __shared__ uint4 cand_in[TILE_THREADS];       // (colour, disparity bits, boundary count, inlier flag) of a queued pixel
-  __shared__ int dec_label[TILE_THREADS];
-  __shared__ unsigned short dec_aux[TILE_THREADS];   // boundary count | inlier << 8
-  const int c = x - xs0;                                 // column of the pixel in the tile (1 .. 62 when ok)
+  // ---- decide on the pass-start state
+  const int c = x - xs0;                                 // column of the pixel in the staged rows (1 .. 62 when ok)
   Decision d;
   d.index = d.new_index = -1; d.b = 0; d.inlier = 0; d.prev_inlier = 0;
   float dv = 0.f;
-  const SpTile<DISP> src = {w};
-  bool cand = false;
+  int nl[4] = {-1, -1, -1, -1};
   if (ok) {
-    d.index = d.new_index = lab[2 * wrp + 1][co + c];
-    d.inlier = 0xff;
-    if (DISP) {                                          // every active pixel re-tests its own plane (tps_decide, same arithmetic)
-      dv = pin.disp;
-      d.prev_inlier = pin.inlier;
-      const float4 th = src.get(d.index).theta_b;
-      const float dp = th.x * (float)x + th.y * (float)y + th.z;
-      const float e = (dp - dv) * (dp - dv);
-      if (!isfinite(e) || e > a.thresh_disp || dp < 0.f) d.inlier = 0;
-    }
-    cand = pin.bounds != 0;
-    if (cand) {
-      cand_in[tid] = make_uint4(*reinterpret_cast<const unsigned*>(&pin.col), __float_as_uint(pin.disp),
-                                (unsigned)pin.bounds, (unsigned)pin.inlier);   // the count can be negative: keep all 32 bits
-    }
-  }
-  const unsigned cmask = __ballot_sync(0xffffffffu, cand);
-  if (lane == 0) cand_count[wrp] = __popc(cmask);
-  __syncthreads();
-  int before = 0, ncand = 0;
-#pragma unroll
-  for (int k = 0; k < TILE_ROWS; k++) {
-    const int n = cand_count[k];
-    if (k < wrp) before += n;
-    ncand += n;
-  }
-  if (cand) cand_list[before + __popc(cmask & ((1u << lane) - 1u))] = (unsigned char)tid;
-  __syncthreads();
-  if (tid < ncand) {
-    // the queued pixel: its place in the tile gives back its coordinates, the staged rows its neighbourhood
-    const int s_tid = cand_list[tid];
-    const int s_lane = s_tid & 31, s_wrp = s_tid >> 5;
-    const int s_rx = (OX ? 2 * (q0 + (s_lane >> 1)) : 2 * (q0 + (s_lane >> 1)) - 1) + (s_lane & 1);
-    const int sx = 2 * s_rx + ((s_rx + OX) & 1);
-    const int sy = 2 * (ry0 + s_wrp) + OY;
-    const int sc = sx - xs0;
-    PixelIn sin;
-    const uint4 packed = cand_in[s_tid];
-    sin.col = *reinterpret_cast<const uchar4*>(&packed.x);
-    sin.disp = __uint_as_float(packed.y);
-    sin.bounds = (int)packed.z;
-    sin.inlier = (unsigned char)packed.w;
     int L[3][4];
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
-      for (int k = 0; k < 3; k++) L[r][k] = lab[2 * s_wrp + r][co + sc - 1 + k];
+      for (int k = 0; k < 3; k++) L[r][k] = lab[2 * wrp + r][co + c - 1 + k];
     L[0][3] = L[1][3] = L[2][3] = -1;
-    Decision sd;
-    float sdv;
-    tps_decide<DISP>(a, src, sin, sx, sy, L, 1, sd, sdv);
-    dec_label[s_tid] = sd.new_index;
-    dec_aux[s_tid] = (unsigned short)((sd.b & 0xff) | (sd.inlier << 8));
-  }
-  __syncthreads();
-  int nl[4] = {-1, -1, -1, -1};
-  if (cand) {
-    d.new_index = dec_label[tid];
-    const unsigned short aux = dec_aux[tid];
-    d.b = aux & 0xff;
-    d.inlier = (unsigned char)(aux >> 8);
-    if (d.new_index != d.index) {                        // the neighbourhood the apply phase walks
-      const int r0 = 2 * wrp, cc = co + c;
-      nl[0] = lab[r0][cc]; nl[1] = lab[r0 + 1][cc - 1]; nl[2] = lab[r0 + 1][cc + 1]; nl[3] = lab[r0 + 2][cc];   // up, left, right, down
-    }
+    const SpTile<DISP> src = {w};
+    tps_decide<DISP>(a, src, pin, x, y, L, 1, d, dv);
+    nl[0] = L[0][1]; nl[1] = L[1][0]; nl[2] = L[1][2]; nl[3] = L[2][1];   // up, left, right, down
   }
   const bool moved = ok && d.new_index != d.index;
 
