@@ -251,3 +251,49 @@ def test_one_launch_registration_equals_multi_launch(orc, monkeypatch):
     assert any(a[1] == 1 for a in pa)                    # registrations were valid, i.e. the poses above moved
     assert ma.n == mb.n and np.array_equal(ma.positions, mb.positions) and np.array_equal(ma.confidences, mb.confidences)
     assert np.array_equal(ma.orientations, mb.orientations) and np.array_equal(ma.shapes, mb.shapes)
+
+
+def test_stage_timing_prepare_and_idle_guard(orc):
+    """SSF_FLAG_STAGE_TIMING fills the per-stage breakdown (and changes no result), ssf_prepare builds the graphs
+    up front, and while frames are in flight every entry point except submit / wait / the pure getters refuses."""
+    from supersurfel_fusion_b200 import CamParam, SsfError, SupersurfelFusion
+    from supersurfel_fusion_b200.engine import SSF_FLAG_STAGE_TIMING
+    seq = SyntheticSequence(width=320, height=240, seed=12)
+    cam = CamParam(*seq.cam_param())
+    params = dict(TUM_PARAMS, nb_supersurfels_max=20000)
+    frames = [seq.frame(k) for k in range(5)]
+    plain = SupersurfelFusion().initialize(cam, **params)
+    timed = SupersurfelFusion().initialize(cam, **params).prepare(SSF_FLAG_STAGE_TIMING)
+    for rgb, depth in frames:
+        sp = plain.processFrame(rgb, depth)
+        st = timed.processFrame(rgb, depth, flags=SSF_FLAG_STAGE_TIMING)
+        assert all(sp[k] == 0.0 for k in ("ms_ingest", "ms_segmentation", "ms_extraction", "ms_registration", "ms_fusion"))
+        parts = [st[k] for k in ("ms_ingest", "ms_segmentation", "ms_extraction", "ms_registration", "ms_fusion")]
+        assert all(p > 0.0 for p in parts), parts
+        assert 0.7 * st["gpu_ms"] <= sum(parts) <= 1.05 * st["gpu_ms"], (parts, st["gpu_ms"])
+        assert st["ms_segmentation"] == max(parts)
+        assert np.array_equal(plain.getPose()[1], timed.getPose()[1]) and sp["nb_supersurfels"] == st["nb_supersurfels"]
+    # frames in flight: the rest of the surface answers SSF_ERR_STATE and leaves the device alone
+    pipe = SupersurfelFusion().initialize(cam, **params).prepare()
+    pipe.submitFrame(*frames[0])
+    pipe.submitFrame(*frames[1])
+    for call in (pipe.getPose, pipe.getModel, pipe.getFrame, pipe.getSegmentation, pipe.fuse, pipe.icp,
+                 pipe.generateSupersurfels, lambda: pipe.setStamp(3), lambda: pipe.setPose(np.eye(3), np.zeros(3)),
+                 lambda: pipe.transformModel(np.eye(3), np.zeros(3)), lambda: pipe.tpsSegment(*frames[0]),
+                 lambda: pipe.invalidateFrameSupersurfels(np.zeros(pipe.nbSuperpixels, np.uint8)), pipe.getStamp):
+        with pytest.raises(SsfError, match="SSF_ERR_STATE"):
+            call()
+    assert pipe.pipelineDepth() >= 1 and pipe.getFrameStats() is not None      # pure getters still answer
+    s0, R0, t0 = pipe.waitFrame()
+    s1, R1, t1 = pipe.waitFrame()
+    # ... and nothing above disturbed the two frames
+    ref = SupersurfelFusion().initialize(cam, **params)
+    ref.processFrame(*frames[0]); ref.processFrame(*frames[1])
+    assert np.array_equal(ref.getPose()[1], t1) and s1["nb_supersurfels"] == ref.getCounts()[0]
+    # submitFrame validates its inputs like processFrame does
+    with pytest.raises(SsfError):
+        pipe.submitFrame(frames[0][0], frames[0][1].astype(np.float64))
+    with pytest.raises(SsfError):
+        pipe.submitFrame(frames[0][0][:100], frames[0][1][:100])
+    for e in (plain, timed, pipe, ref):
+        e.close()
