@@ -467,9 +467,9 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   A(dalloc(&e->filt_a, (size_t)S * 16)); A(dalloc(&e->filt_b, (size_t)S * 8));   // filt_a also serves as the 11-plane scratch of tps_filter_kernel<false>
   A(dalloc(&e->xsums, (size_t)S * 16));
   A(dalloc(&e->tps_barrier, (size_t)32));
-  if (getenv("SSF_TPS_TRACE") && e->tps_grid > 0) {
+  if (getenv("SSF_TPS_TRACE")) {
     char* t = nullptr;
-    A(dalloc(&t, tps_trace_bytes(e->tps_grid)));
+    A(dalloc(&t, tps_trace_bytes(e->tps_grid > 148 ? e->tps_grid : 148)));   // also holds 8 stamps per CTA of a fused pass
     e->tps_trace = reinterpret_cast<unsigned long long*>(t);
   }
   e->frame.stride = round4(S);
@@ -1219,7 +1219,7 @@ int ssf_tps_segment(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const fl
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   SSF_LAUNCH_OK(e);
   if (e->tps_trace) {   // profiling aid: dump the per-CTA phase timestamps of this call
-    std::vector<unsigned long long> host(tps_trace_bytes(e->tps_grid) / 8);
+    std::vector<unsigned long long> host(tps_trace_bytes(e->tps_grid > 148 ? e->tps_grid : 148) / 8);
     cudaMemcpy(host.data(), e->tps_trace, host.size() * 8, cudaMemcpyDeviceToHost);
     if (FILE* f = fopen(getenv("SSF_TPS_TRACE"), "wb")) { fwrite(host.data(), 8, host.size(), f); fclose(f); }
     cudaMemset(e->tps_trace, 0, host.size() * 8);

@@ -55,6 +55,7 @@ struct TpsArgs {
   SpSums* sums_zero;
   unsigned long long gx_magic;   // ceil(2^32 / gx): k / gx == (k * gx_magic) >> 32 for every superpixel id k
   unsigned long long cell_magic; // ceil(2^32 / cell), the same for pixel coordinates
+  long long* trace;        // profiling aid (SSF_TPS_TRACE): per-CTA clock64 stamps of the fused pass, else NULL
 };
 
 static TpsArgs tps_args(const Engine* e) {
@@ -72,6 +73,7 @@ static TpsArgs tps_args(const Engine* e) {
   a.sums_nxt = a.sums_zero = nullptr;
   a.gx_magic = (0x100000000ull + (unsigned)e->gx - 1) / (unsigned)e->gx;
   a.cell_magic = (0x100000000ull + (unsigned)e->cfg.cell_size - 1) / (unsigned)e->cfg.cell_size;
+  a.trace = reinterpret_cast<long long*>(e->tps_trace);
   return a;
 }
 
@@ -512,6 +514,8 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
   const int tid = threadIdx.x;
   const int lane = tid & 31, wrp = tid >> 5;
   const SpSums* cur = a.sums;
+  long long* tr = (a.trace && tid == 0) ? a.trace + 8 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (tr) tr[0] = clock64();
 
   // The kernel is a chain of dependent latencies (L2 round trip -> means -> decisions -> atomics), so
   // it is written to have every global load of the pass in flight before anything waits: first the
@@ -620,6 +624,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
   pin.bounds = 0; pin.col = make_uchar4(0, 0, 0, 0); pin.disp = 0.f; pin.inlier = 0;
   if (ok) pin = tps_fetch_pixel<DISP>(a, p);
 
+  if (tr) tr[1] = clock64();
   // ---- means (and planes) of the window from the quiescent sums: the merge kernel's arithmetic,
   // split over two threads per superpixel so that the divisions of the means and the dependent
   // divisions of the plane solve run side by side
@@ -644,6 +649,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
     Superpixel& s = win[slot];
     s.theta_b.x = tx; s.theta_b.y = ty; s.theta_b.z = tz;
   }
+  if (tr) tr[2] = clock64();
   if (TMA) {
     __syncthreads();                       // the barrier was initialised by thread 0: nobody polls it before this
     mbar_wait(&lab_bar, 0);
@@ -670,6 +676,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
   }
   __syncthreads();
 
+  if (tr) tr[3] = clock64();
   // ---- decide on the pass-start state
   const int c = x - xs0;                                 // column of the pixel in the staged rows (1 .. 62 when ok)
   Decision d;
@@ -688,6 +695,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
     nl[0] = L[0][1]; nl[1] = L[1][0]; nl[2] = L[1][2]; nl[3] = L[2][1];   // up, left, right, down
   }
   const bool moved = ok && d.new_index != d.index;
+  if (tr) tr[4] = clock64();
 
   // ---- apply.  Everything read above is pass-start state: the only pixels written in this pass
   // are active ones, each by its own thread, and the only active 4-neighbour of an active pixel is
@@ -744,6 +752,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
     else if (from_partner != 0) a.bound[p] = pin.bounds + from_partner; // only this thread touches it
   }
 
+  if (tr) tr[5] = clock64();
   // ---- buffer rotation for the superpixels this CTA owns (last: nothing waits for it)
   {
     const int nb = gridDim.x * gridDim.y;
@@ -758,6 +767,7 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
       reinterpret_cast<long long*>(a.sums_zero)[off] = 0;
     }
   }
+  if (tr) tr[6] = clock64();
 }
 
 // ---- RANSAC plane initialisation (TPS_RGBD_kernels.cu:318-467, 112-190) --------------
