@@ -591,6 +591,17 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
     }
   }
 
+  // ---- buffer rotation, first half: the owner's words of `cur` are fetched now by the warps that compute no
+  // means (their L2 round trip overlaps everything else); carried into `nxt` at the very end
+  constexpr int ROT_FIRST = TILE_THREADS - 64;             // threads 192 .. 255 hold one word each per round
+  const int rot_nb = gridDim.x * gridDim.y;
+  const int rot_per = (a.S + rot_nb - 1) / rot_nb;
+  const int rot_s0 = (blockIdx.y * gridDim.x + blockIdx.x) * rot_per;
+  const int rot_words = max(0, min(a.S, rot_s0 + rot_per) - rot_s0) * 16;
+  long long rot_v = 0;
+  const bool rot_mine = tid >= ROT_FIRST && tid - ROT_FIRST < rot_words;
+  if (rot_mine) rot_v = reinterpret_cast<const long long*>(cur)[(size_t)rot_s0 * 16 + (tid - ROT_FIRST)];
+
   // ---- label rows (coalesced 8-byte loads; xs0 is even and W need not be): all in flight, stored later
   int2 lv[3];
 #pragma unroll
@@ -753,15 +764,15 @@ __global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, 
   }
 
   if (tr) tr[5] = clock64();
-  // ---- buffer rotation for the superpixels this CTA owns (last: nothing waits for it)
+  // ---- buffer rotation, second half (last: nothing waits for it)
   {
-    const int nb = gridDim.x * gridDim.y;
-    const int b = blockIdx.y * gridDim.x + blockIdx.x;
-    const int per = (a.S + nb - 1) / nb;
-    const int s0 = b * per, s1 = min(a.S, s0 + per);
-    const int words = (s1 - s0) * 16;
-    for (int i = tid; i < words; i += TILE_THREADS) {
-      const size_t off = (size_t)s0 * 16 + i;
+    if (rot_mine) {
+      const size_t off = (size_t)rot_s0 * 16 + (tid - ROT_FIRST);
+      if (rot_v != 0) add64(reinterpret_cast<long long*>(a.sums_nxt) + off, rot_v);
+      reinterpret_cast<long long*>(a.sums_zero)[off] = 0;
+    }
+    for (int i = 64 + tid; i < rot_words; i += TILE_THREADS) {     // more than 4 superpixels per CTA (coarse grids)
+      const size_t off = (size_t)rot_s0 * 16 + i;
       const long long v = reinterpret_cast<const long long*>(cur)[off];
       if (v != 0) add64(reinterpret_cast<long long*>(a.sums_nxt) + off, v);
       reinterpret_cast<long long*>(a.sums_zero)[off] = 0;
