@@ -306,10 +306,20 @@ __global__ void __launch_bounds__(INS_THREADS) insert_kernel(SurfelSet model, Su
   const int stamp = counters->stamp;
   if (tid == 0) running = 0;
   __syncthreads();
-  for (int base = 0; base < S; base += INS_THREADS) {
-    const int f = base + tid;
-    const int flag = (f < S && frame.plane(P_CONF)[f] > 0.0f && !matched[f]) ? 1 : 0;
-    int incl = flag;
+  // four consecutive frame supersurfels per thread and round: 640x480 (S = 1200) is ONE round of flags ->
+  // block scan -> writes instead of two
+  constexpr int INS_ITEMS = 4;
+  for (int base = 0; base < S; base += INS_THREADS * INS_ITEMS) {
+    const int f0 = base + tid * INS_ITEMS;
+    int flag[INS_ITEMS];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < INS_ITEMS; j++) {
+      const int f = f0 + j;
+      flag[j] = (f < S && frame.plane(P_CONF)[f] > 0.0f && !matched[f]) ? 1 : 0;
+      mine += flag[j];
+    }
+    int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -327,10 +337,14 @@ __global__ void __launch_bounds__(INS_THREADS) insert_kernel(SurfelSet model, Su
       warp_sums[lane] = v;  // inclusive
     }
     __syncthreads();
-    const int before = running + (wid > 0 ? warp_sums[wid - 1] : 0) + incl - flag;
+    int before = running + (wid > 0 ? warp_sums[wid - 1] : 0) + incl - mine;
     const int total = warp_sums[INS_THREADS / 32 - 1];
-    if (flag) {
+#pragma unroll
+    for (int j = 0; j < INS_ITEMS; j++) {
+      if (!flag[j]) continue;
+      const int f = f0 + j;
       const int k = nb0 + before;
+      before++;
       if (k < cap) {
         stv(model, P_POS, k, R * ldv(frame, P_POS, f) + t);
         sts(model, k, rotate_sym(R, lds(frame, f)));

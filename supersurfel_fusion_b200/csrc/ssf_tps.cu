@@ -888,13 +888,28 @@ __global__ void tps_eval_samples_kernel(TpsArgs a, const float4* samples, int* v
 
 __device__ __forceinline__ void tps_select_item(const TpsArgs& a, float4* samples, const int* votes, int nbSamples,
                                                 int idx) {
-  float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = 0; k < nbSamples; k++) {
-    float4 th = samples[(size_t)idx * nbSamples + k];
-    th.w = (float)votes[(size_t)idx * nbSamples + k];
-    samples[(size_t)idx * nbSamples + k].w = th.w;
-    if (th.w > best.w) best = th;
+  // first strict maximum of the votes (TPS_RGBD_kernels.cu:446-456).  The votes are fetched eight at a time so
+  // that the loop is two L2 round trips for the usual 16 samples instead of one per sample; the winning plane is
+  // read afterwards, the vote counts go back into the samples' fourth component for ssf_get_ransac_samples.
+  const int* v = votes + (size_t)idx * nbSamples;
+  float4* smp = samples + (size_t)idx * nbSamples;
+  float best_w = 0.f;
+  int best_k = -1;
+  for (int k0 = 0; k0 < nbSamples; k0 += 8) {
+    int cnt[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) cnt[j] = (k0 + j < nbSamples) ? v[k0 + j] : 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (k0 + j < nbSamples) {
+        const float w = (float)cnt[j];
+        smp[k0 + j].w = w;
+        if (w > best_w) { best_w = w; best_k = k0 + j; }
+      }
+    }
   }
+  float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (best_k >= 0) best = smp[best_k];
   a.sp[idx].theta_b.x = best.x; a.sp[idx].theta_b.y = best.y; a.sp[idx].theta_b.z = best.z;
   SpSums* c = &a.sums[idx];
   c->dx = c->dy = c->dxx = c->dyy = c->dxy = c->dn = c->dxd = c->dyd = c->dd = 0;
