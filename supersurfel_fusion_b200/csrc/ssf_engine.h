@@ -168,6 +168,7 @@ struct Engine {
   float* filt_b;
   int tps_tma;           // 1: the fused pass stages its label tile with a 2-D tensor-map TMA copy (SSF_TPS_TMA; needs W % 4 == 0)
   alignas(64) unsigned char label_map[SSF_SLOTS][128];   // CUtensorMap over each slot's label image
+  int tps_occ;           // resident CTAs per SM the fused pass is compiled for (SSF_TPS_OCC: 3 = unconstrained, 4)
   int tps_fused;         // 1 (default): relabelling passes derive the means themselves, no merge launches (SSF_TPS_FUSED)
   int tps_persistent;    // 1: whole segmentation is one cooperative kernel
   int tps_grid;          // its grid (one CTA per SM)

@@ -504,8 +504,10 @@ __device__ __forceinline__ int div_magic(int a, unsigned long long magic) {
 // fault), so the box starts at the multiple of four at or below the tile's first column (the tile starts at
 // 4 q0 - 2 in the OX = 0 passes) and is four columns wider than the tile; `co` is where the tile begins
 // inside the staged rows.  Needs a 16-byte row pitch (W % 4 == 0), otherwise the loads below do the job.
-template <bool DISP, bool TMA>
-__global__ void __launch_bounds__(TILE_THREADS) tps_pass_tile_kernel(TpsArgs a, int OX, int OY,
+// MINB = resident CTAs per SM the kernel is compiled for (SSF_TPS_OCC): 4 caps the colour + disparity variant at
+// 64 registers (a few spilled words) so that the passes of more frames in flight fit on an SM side by side.
+template <bool DISP, bool TMA, int MINB>
+__global__ void __launch_bounds__(TILE_THREADS, MINB) tps_pass_tile_kernel(TpsArgs a, int OX, int OY,
                                                                      const __grid_constant__ CUtensorMap label_map) {
   pdl_sync();
   __shared__ __align__(128) int lab[TILE_LROWS][TILE_SCOLS];
@@ -1424,8 +1426,13 @@ static void launch_pass_fused(Engine* e, TpsArgs a, int p, int OX, int OY) {
   a.sums_zero = sums_buffer(e, p + 2);
   dim3 grd(cdiv(pairs, TILE_LANES / 2), cdiv(a.raw_h, TILE_ROWS));
   const CUtensorMap& map = *reinterpret_cast<const CUtensorMap*>(e->label_map[e->cur_slot]);
-  if (e->tps_tma) launch_pdl(e, tps_pass_tile_kernel<DISP, true>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
-  else launch_pdl(e, tps_pass_tile_kernel<DISP, false>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+  if (e->tps_occ >= 4) {
+    if (e->tps_tma) launch_pdl(e, tps_pass_tile_kernel<DISP, true, 4>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+    else launch_pdl(e, tps_pass_tile_kernel<DISP, false, 4>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+  } else {
+    if (e->tps_tma) launch_pdl(e, tps_pass_tile_kernel<DISP, true, 1>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+    else launch_pdl(e, tps_pass_tile_kernel<DISP, false, 1>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+  }
   e->launches += 1;
 }
 
