@@ -1430,8 +1430,8 @@ static void launch_pass_fused(Engine* e, TpsArgs a, int p, int OX, int OY) {
     if (e->tps_tma) launch_pdl(e, tps_pass_tile_kernel<DISP, true, 4>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
     else launch_pdl(e, tps_pass_tile_kernel<DISP, false, 4>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
   } else {
-    if (e->tps_tma) launch_pdl(e, tps_pass_tile_kernel<DISP, true, 1>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
-    else launch_pdl(e, tps_pass_tile_kernel<DISP, false, 1>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+    if (e->tps_tma) launch_pdl(e, tps_pass_tile_kernel<DISP, true, 3>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+    else launch_pdl(e, tps_pass_tile_kernel<DISP, false, 3>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
   }
   e->launches += 1;
 }
