@@ -434,7 +434,7 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   // measured on B200 at VGA it is ~6 % slower per frame than the graph of small kernels
   // (0.602 vs 0.559 ms; per pass ~1.4 us cache fill + ~3.7 us relabel + ~1.7 us barrier for the
   // colour passes, 3.2 + 4.1 + 2.4 us with the disparity plane), see DESIGN.md section 3.
-  e->tps_occ = 4;   // measured on B200 (same box, 300-frame windows): 5800 vs 5480 frames/s pipelined, 0.468 vs 0.493 ms synchronous
+  e->tps_occ = 3;   // 80 registers, no spills; 4 (64 registers) measured the same on B200: 5790 vs 5780 frames/s, 0.466 vs 0.467 ms
   if (const char* v = getenv("SSF_TPS_OCC")) e->tps_occ = atoi(v);
   e->tps_fused = 1;
   if (const char* v = getenv("SSF_TPS_FUSED")) e->tps_fused = atoi(v) != 0;   // 0: round-1 pass + merge launches (A/B)
