@@ -24,7 +24,8 @@ class SsfError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libssf.so")
+    """The in-tree library; SSF_LIB points at another build of the same sources (compile-time A/B experiments)."""
+    return os.environ.get("SSF_LIB") or os.path.join(_HERE, "libssf.so")
 
 
 class CamParam(C.Structure):

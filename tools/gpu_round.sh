@@ -22,16 +22,15 @@ ref)
   timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err
   cat $OUT/bench_ref_$TAG.json ;;
 launches)
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 300 --csv --log-file $OUT/launches_$TAG.csv \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 250 -c 130 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 6 --warmup 3 --reps 1 --skip-extras --no-pipeline > $OUT/ncu_launches_$TAG.log 2>&1 ;;
 icp)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:icp_system -s 4 -c 1 -f -o $OUT/icp_$TAG \
     python bench.py --roofline-only > $OUT/ncu_icp_$TAG.log 2>&1 ;;
-tps)      # full captures of the segmentation kernels inside the synchronous frame graph (frame 2+: -s skips frame 1)
-  for K in tps_pass_kernel:70 tps_merge_kernel:70 tps_filter_kernel:2 tps_init_samples_kernel:2 tps_persistent_kernel:2; do
+tps)      # full captures of the segmentation / registration kernels inside the synchronous frame graph (-s skips frame 1)
+  for K in tps_pass_tile_kernel:110 tps_filter_kernel:2 tps_init_samples_kernel:2 icp_loop_kernel:2; do
     N=${K%%:*}; SK=${K##*:}
-    PERSIST=0; [ $N = tps_persistent_kernel ] && PERSIST=1
-    SSF_TPS_PERSISTENT=$PERSIST timeout 300 ncu --set full --clock-control none --import-source on -k regex:$N -s $SK -c 1 -f -o $OUT/${N}_$TAG \
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:$N -s $SK -c 1 -f -o $OUT/${N}_$TAG \
       python bench.py --steps 6 --warmup 3 --reps 1 --skip-extras --no-pipeline > $OUT/ncu_${N}_$TAG.log 2>&1
   done ;;
 trace)
