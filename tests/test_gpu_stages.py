@@ -169,10 +169,11 @@ def test_icp_starved_is_invalid(orc, warm_state):
 
 
 @pytest.mark.parametrize("n_src,stages,occ", [(600000, "1", "3"), (600003, "1", "3"), (600000, "3", "3"),
-                                              (600001, "2", "4"), (600000, "1", "5")])
+                                              (600001, "2", "4"), (600000, "1", "5"), (600002, "-2", "3"),
+                                              (600000, "-3", "4"), (600000, "1", "2")])
 def test_icp_large_problem_matches_oracle(orc, monkeypatch, n_src, stages, occ):
     """Streaming regime: more source supersurfels than one wave of CTAs (grid-stride path), ragged
-    slice ends, and every tuning variant of the system kernel (TMA ring depth, register budget)."""
+    slice ends, and every tuning variant of the system kernel (TMA ring depth, thread-private cp.async ring, register budget)."""
     from supersurfel_fusion_b200 import CamParam, SupersurfelFusion
     monkeypatch.setenv("SSF_ICP_STAGES", stages)
     monkeypatch.setenv("SSF_ICP_OCC", occ)
