@@ -428,7 +428,6 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   e->icp_stages = 1;
   if (const char* v = getenv("SSF_ICP_STAGES")) e->icp_stages = atoi(v);   // tuning knob: 1 (no ring) .. 4 TMA ring per CTA; -2 .. -4 thread-private cp.async ring
   e->icp_stages = icp_configure(e->icp_stages);
-  e->icp_ring_lockstep = getenv("SSF_ICP_RING_LOCKSTEP") ? atoi(getenv("SSF_ICP_RING_LOCKSTEP")) : 0;
   tps_configure();
   e->tps_grid = tps_persistent_grid(device, e->gx, e->gy, cfg->cell_size, e->H, cfg->seg_iter, &e->tps_cache_slots);
   // The one-kernel (cooperative, band-owned) form of the segmentation is kept as an option:

@@ -192,7 +192,6 @@ struct Engine {
   int pdl;               // 1: kernels are chained by programmatic dependent launch (SSF_PDL, default 0: measured slower)
   int icp_occ;           // resident CTAs per SM the system kernel is compiled for
   int icp_stages;        // staging of the streamed planes (SSF_ICP_STAGES): 1 direct loads (default), 2..4 TMA ring, < 0 pipelined kernel
-  int icp_ring_lockstep; // SSF_ICP_RING_LOCKSTEP=1: the round-1 ring inside icp_system_kernel (one __syncthreads() per chunk)
   int icp_debug;         // profiling knob, see IcpArgs::debug
   int icp_loop;          // 1 (default): small visible models register in one cluster launch (SSF_ICP_LOOP=0: never)
   // tile-parallel registration over peer memory
