@@ -246,7 +246,9 @@ static int ensure_frame_graph(EngineImpl* e, int gi, bool upload) {
   cudaGraph_t g;
   const uint64_t before = e->launches;
   SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  e->pdl_now = e->pdl;
   enqueue_frame(e, (gi & 1) != 0, (gi & 2) != 0, (gi & 4) != 0);
+  e->pdl_now = 0;
   SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
   e->launches_per_frame[gi] = e->launches - before;
   e->launches = before;
@@ -420,8 +422,11 @@ int ssf_create(const SsfConfig* cfg, int device, SsfHandle* out) {
   const int need_blocks = (e->cap + icp_chunk_size() - 1) / icp_chunk_size();
   // measured on B200 at VGA (300 frames): 0.563 ms/frame without, 0.582 ms/frame with PDL edges in the
   // frame graph -- the chain is bound by each kernel's own dependent L2 round trips, not by launch gaps
-  e->pdl = 0;
-  if (const char* v = getenv("SSF_PDL")) e->pdl = atoi(v) != 0;
+  e->pdl = 3;
+  e->pdl_pipe = 0;
+  e->pdl_now = 0;
+  if (const char* v = getenv("SSF_PDL")) e->pdl = atoi(v);
+  if (const char* v = getenv("SSF_PDL_PIPE")) e->pdl_pipe = atoi(v);
   e->icp_occ = 3;
   if (const char* v = getenv("SSF_ICP_OCC")) e->icp_occ = atoi(v);   // tuning knob: 2 .. 5
   if (e->icp_occ < 2 || e->icp_occ > 5) e->icp_occ = 3;
@@ -742,7 +747,9 @@ static int capture_stage(EngineImpl* e, int slot, int stage, int gi) {
   cudaGraph_t g;
   const uint64_t before = e->launches;
   SSF_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  e->pdl_now = e->pdl_pipe;
   enqueue_steps(e, e->stage_first[stage], e->stage_first[stage + 1], (gi & 1) != 0, true, e->d_report2[slot], false, (gi & 2) != 0);
+  e->pdl_now = 0;
   SSF_CUDA(e, cudaStreamEndCapture(e->stream, &g));
   e->stage_launches[slot][stage][gi] = e->launches - before;
   e->launches = before;

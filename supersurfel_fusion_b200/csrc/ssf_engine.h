@@ -189,7 +189,11 @@ struct Engine {
   IcpState* icp;
   float* icp_partials;   // [grid][32]
   int icp_grid;
-  int pdl;               // 1: kernels are chained by programmatic dependent launch (SSF_PDL, default 0: measured slower)
+  // Programmatic dependent launch (SSF_PDL) inside the SYNCHRONOUS frame graph: 0 plain graph edges; 1 every kernel
+  // lets its successor launch at its top; 2 as 1, but the fused segmentation pass triggers only after its decisions;
+  // 3 only the pass -> pass edges are programmatic (late trigger).  pdl_now is the mode of the launches being
+  // enqueued right now (0 outside that graph's capture: the pipelined stage graphs measured slower with any of them)
+  int pdl, pdl_pipe, pdl_now;
   int icp_occ;           // resident CTAs per SM the system kernel is compiled for
   int icp_stages;        // staging of the streamed planes (SSF_ICP_STAGES): 1 direct loads (default), 2..4 TMA ring, < 0 pipelined kernel
   int icp_debug;         // profiling knob, see IcpArgs::debug
@@ -212,12 +216,13 @@ struct Engine {
   size_t scratch_bytes;
 };
 
-// Every kernel of the library is launched through here.  With e->pdl the launch carries
-// cudaLaunchAttributeProgrammaticStreamSerialization, which (also under stream capture, as
-// a programmatic graph edge) lets the kernel start while its predecessor drains; the
-// kernels order themselves with pdl_sync() (ssf_math.cuh).
+// Every kernel of the library is launched through here.  With programmatic dependent launch on, the
+// launch carries cudaLaunchAttributeProgrammaticStreamSerialization, which (also under stream capture,
+// as a programmatic graph edge) lets the kernel start while its predecessor drains; the kernels order
+// themselves with pdl_wait() / pdl_trigger() (ssf_math.cuh).  pass_edge: the launch is a fused
+// segmentation pass (the only programmatic edges of mode 3).
 template <typename... P, typename... A>
-inline void launch_pdl(Engine* e, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, A&&... args) {
+inline void launch_kernel(Engine* e, bool pass_edge, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, A&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -227,9 +232,13 @@ inline void launch_pdl(Engine* e, void (*kernel)(P...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = e->pdl ? 1 : 0;
+  cfg.numAttrs = (e->pdl_now == 1 || e->pdl_now == 2 || (e->pdl_now == 3 && pass_edge)) ? 1 : 0;
   const cudaError_t rc = cudaLaunchKernelEx(&cfg, kernel, P(args)...);
   if (rc != cudaSuccess && e->launch_err == cudaSuccess) e->launch_err = rc;   // surfaced by the entry point (launch_status)
+}
+template <typename... P, typename... A>
+inline void launch_pdl(Engine* e, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, A&&... args) {
+  launch_kernel(e, false, kernel, grid, block, smem, static_cast<A&&>(args)...);
 }
 
 // ---- stage launchers (each enqueues on e->stream, no host sync) -----------------

@@ -13,15 +13,19 @@
 
 namespace ssf {
 
-// Programmatic dependent launch (PDL), an option (SSF_PDL=1): the frame is a chain of ~110
-// small dependent kernels.  Every kernel starts by (1) letting the next kernel in
-// the stream / graph begin launching right away and (2) waiting until every kernel before
-// it has completed and its writes are visible -- so the next kernel's CTAs are already
-// resident and parked at their own wait when this one finishes.  Both instructions are
-// no-ops for a kernel launched without the attribute (see launch_pdl, ssf_engine.h).
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-serialisation attribute may
+// start once every CTA of its predecessor has executed griddepcontrol.launch_dependents (or exited), and must
+// execute griddepcontrol.wait before it touches anything the predecessor wrote (the wait returns when the
+// predecessor has completed and its writes are visible).  Both instructions are no-ops for a kernel launched
+// without the attribute (launch_kernel, ssf_engine.h).  Measured on the synchronous VGA frame (SSF_PDL,
+// tools/pdl_ab.sh): a trigger at the TOP of every kernel loses (0.470 vs 0.465 ms: the successor's CTAs take SM
+// slots while the predecessor still needs them), but the 92 fused segmentation passes triggering AFTER their
+// decisions and waiting AFTER their argument arithmetic gain 7 % (0.432 ms): that is the default (mode 3).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() {
-  asm volatile("griddepcontrol.launch_dependents;");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_trigger();
+  pdl_wait();
 }
 
 // ---- TMA bulk copies + mbarrier (the async-proxy path global -> shared memory) ---------

@@ -42,6 +42,7 @@ struct TpsArgs {
   int raw_w, raw_h;        // thread extents of the reference launch (TPS_RGBD.cu:185-186)
   int min_size;
   int debug;               // profiling knob, 0 in production
+  int pdl_late;            // SSF_PDL 2 / 3: the fused pass lets its successor launch only once its decisions are made
   float lambda_pos, lambda_bound, lambda_size, lambda_disp, thresh_disp;
   uchar4* rgba;
   float* disp;
@@ -74,6 +75,7 @@ static TpsArgs tps_args(const Engine* e) {
   a.gx_magic = (0x100000000ull + (unsigned)e->gx - 1) / (unsigned)e->gx;
   a.cell_magic = (0x100000000ull + (unsigned)e->cfg.cell_size - 1) / (unsigned)e->cfg.cell_size;
   a.trace = reinterpret_cast<long long*>(e->tps_trace);
+  a.pdl_late = e->pdl_now >= 2;
   return a;
 }
 
@@ -509,7 +511,12 @@ __device__ __forceinline__ int div_magic(int a, unsigned long long magic) {
 template <bool DISP, bool TMA, int MINB>
 __global__ void __launch_bounds__(TILE_THREADS, MINB) tps_pass_tile_kernel(TpsArgs a, int OX, int OY,
                                                                      const __grid_constant__ CUtensorMap label_map) {
-  pdl_sync();
+  // SSF_PDL=2: the successor may launch once this grid has decided (below), and a grid waits for its
+  // predecessor only here, after its CTAs are resident
+  if (!a.pdl_late) {
+    pdl_trigger();
+    pdl_wait();
+  }
   __shared__ __align__(128) int lab[TILE_LROWS][TILE_SCOLS];
   __shared__ __align__(8) uint64_t lab_bar;
   __shared__ Superpixel win[TILE_WIN];
@@ -530,8 +537,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) tps_pass_tile_kernel(TpsAr
   const int y0 = 2 * ry0 + OY;                           // first active row; staged rows start at y0 - 1
   const int co = OX ? 0 : 2;                             // column of the staged rows that holds image column xs0
 
-  if (TMA) {
-    if (tid == 0) {
+  auto stage_labels = [&]() {
+    if (TMA && tid == 0) {
       mbar_init(&lab_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -542,7 +549,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) tps_pass_tile_kernel(TpsAr
           "l"(&label_map), "r"(xs0 - co), "r"(y0 - 1), "r"(smem_u32(&lab_bar))
           : "memory");
     }
-  }
+  };
+  if (!a.pdl_late) stage_labels();
 
   // ---- window of superpixels whose means this tile may need: the grid cells under the tile plus a
   // margin of one cell (boundaries drift a few pixels over the 4 * seg_iter passes); with small
@@ -577,6 +585,12 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) tps_pass_tile_kernel(TpsAr
   if (does_mean || does_plane) {
     const int wr = (int)(((float)slot + 0.5f) * __frcp_rn((float)w.ww));     // slot / ww, exact for these sizes
     wk = (w.wy0 + wr) * a.gx + (w.wx0 + (slot - wr * w.ww));
+  }
+  // late-trigger mode: everything above is arithmetic on kernel arguments and ran while the previous
+  // pass was still applying its decisions; its labels and sums are read from here on
+  if (a.pdl_late) {
+    pdl_wait();
+    stage_labels();
   }
   // 16-byte loads of the half of the record this thread needs
   longlong2 sv[5];
@@ -709,6 +723,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) tps_pass_tile_kernel(TpsAr
   }
   const bool moved = ok && d.new_index != d.index;
   if (tr) tr[4] = clock64();
+  if (a.pdl_late) pdl_trigger();
 
   // ---- apply.  Everything read above is pass-start state: the only pixels written in this pass
   // are active ones, each by its own thread, and the only active 4-neighbour of an active pixel is
@@ -1427,11 +1442,11 @@ static void launch_pass_fused(Engine* e, TpsArgs a, int p, int OX, int OY) {
   dim3 grd(cdiv(pairs, TILE_LANES / 2), cdiv(a.raw_h, TILE_ROWS));
   const CUtensorMap& map = *reinterpret_cast<const CUtensorMap*>(e->label_map[e->cur_slot]);
   if (e->tps_occ >= 4) {
-    if (e->tps_tma) launch_pdl(e, tps_pass_tile_kernel<DISP, true, 4>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
-    else launch_pdl(e, tps_pass_tile_kernel<DISP, false, 4>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+    if (e->tps_tma) launch_kernel(e, true, tps_pass_tile_kernel<DISP, true, 4>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+    else launch_kernel(e, true, tps_pass_tile_kernel<DISP, false, 4>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
   } else {
-    if (e->tps_tma) launch_pdl(e, tps_pass_tile_kernel<DISP, true, 3>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
-    else launch_pdl(e, tps_pass_tile_kernel<DISP, false, 3>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+    if (e->tps_tma) launch_kernel(e, true, tps_pass_tile_kernel<DISP, true, 3>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
+    else launch_kernel(e, true, tps_pass_tile_kernel<DISP, false, 3>, dim3(grd), dim3(TILE_THREADS), 0, a, OX, OY, map);
   }
   e->launches += 1;
 }
