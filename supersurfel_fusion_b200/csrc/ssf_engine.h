@@ -232,7 +232,7 @@ inline void launch_kernel(Engine* e, bool pass_edge, void (*kernel)(P...), dim3 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (e->pdl_now == 1 || e->pdl_now == 2 || (e->pdl_now == 3 && pass_edge)) ? 1 : 0;
+  cfg.numAttrs = (e->pdl_now == 1 || e->pdl_now == 2 || (e->pdl_now >= 3 && pass_edge)) ? 1 : 0;
   const cudaError_t rc = cudaLaunchKernelEx(&cfg, kernel, P(args)...);
   if (rc != cudaSuccess && e->launch_err == cudaSuccess) e->launch_err = rc;   // surfaced by the entry point (launch_status)
 }

@@ -43,6 +43,7 @@ struct TpsArgs {
   int min_size;
   int debug;               // profiling knob, 0 in production
   int pdl_late;            // SSF_PDL 2 / 3: the fused pass lets its successor launch only once its decisions are made
+  int pdl_trig;            // where: 0 after the decisions (default), 1 at the top, 2 once the pass's loads are in flight, 3 after the apply phase (A/B)
   float lambda_pos, lambda_bound, lambda_size, lambda_disp, thresh_disp;
   uchar4* rgba;
   float* disp;
@@ -76,6 +77,7 @@ static TpsArgs tps_args(const Engine* e) {
   a.cell_magic = (0x100000000ull + (unsigned)e->cfg.cell_size - 1) / (unsigned)e->cfg.cell_size;
   a.trace = reinterpret_cast<long long*>(e->tps_trace);
   a.pdl_late = e->pdl_now >= 2;
+  a.pdl_trig = e->pdl_now == 4 ? 1 : e->pdl_now == 5 ? 2 : e->pdl_now == 6 ? 3 : 0;
   return a;
 }
 
@@ -516,6 +518,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) tps_pass_tile_kernel(TpsAr
   if (!a.pdl_late) {
     pdl_trigger();
     pdl_wait();
+  } else if (a.pdl_trig == 1) {
+    pdl_trigger();
   }
   __shared__ __align__(128) int lab[TILE_LROWS][TILE_SCOLS];
   __shared__ __align__(8) uint64_t lab_bar;
@@ -652,6 +656,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) tps_pass_tile_kernel(TpsAr
   if (ok) pin = tps_fetch_pixel<DISP>(a, p);
 
   if (tr) tr[1] = clock64();
+  if (a.pdl_late && a.pdl_trig == 2) pdl_trigger();
   // ---- means (and planes) of the window from the quiescent sums: the merge kernel's arithmetic,
   // split over two threads per superpixel so that the divisions of the means and the dependent
   // divisions of the plane solve run side by side
@@ -723,7 +728,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) tps_pass_tile_kernel(TpsAr
   }
   const bool moved = ok && d.new_index != d.index;
   if (tr) tr[4] = clock64();
-  if (a.pdl_late) pdl_trigger();
+  if (a.pdl_late && a.pdl_trig == 0) pdl_trigger();
 
   // ---- apply.  Everything read above is pass-start state: the only pixels written in this pass
   // are active ones, each by its own thread, and the only active 4-neighbour of an active pixel is
@@ -781,6 +786,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) tps_pass_tile_kernel(TpsAr
   }
 
   if (tr) tr[5] = clock64();
+  if (a.pdl_late && a.pdl_trig == 3) pdl_trigger();
   // ---- buffer rotation, second half (last: nothing waits for it)
   {
     if (rot_mine) {
