@@ -25,7 +25,7 @@ def _torchrun(n, script, *args, port=29533):
     return json.loads(lines[-1])
 
 
-def test_tile_parallel_icp_two_gpus():
+def test_tile_parallel_icp_two_gpus(orc):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     r = _torchrun(2, "tools/tile_icp_check.py", str(1 << 20))
@@ -39,6 +39,17 @@ def test_tile_parallel_icp_two_gpus():
     # the fused peer-memory loop (no NCCL, no host round trip) gives the same pose
     assert r["valid_fused"] and r["iters_fused"] == r["iters_single"]
     assert r["dt_fused"] < 1e-5 and r["dR_fused"] < 1e-5
+    # ... and all three agree with the CPU oracle's loop on the same 2560x1920 problem (configs[4])
+    import numpy as np
+    from supersurfel_fusion_b200.synth import synthetic_icp_problem
+    prob = synthetic_icp_problem(1 << 20, width=2560, height=1920, seed=1234)
+    ok_o, R_o, t_o, st_o = orc.icp(orc.OrcCam(*prob["cam"]), prob["src_pos"], prob["src_col"], prob["src_ori"], prob["tgt_col"],
+                                   prob["tgt_ori"], prob["tgt_conf"], np.array(r["R_init"], np.float32),
+                                   np.array(r["t_init"], np.float32), prob["labels"], prob["depth"])
+    assert ok_o and st_o["iters"] == r["iters_single"]
+    for tag in ("single", "tiled", "fused"):
+        assert np.linalg.norm(np.array(r["t_" + tag], np.float32) - t_o) < 1e-5, tag          # metres (north_star: 1e-4)
+        assert np.abs(np.array(r["R_" + tag], np.float32).reshape(3, 3) - R_o).max() < 1e-5, tag
 
 
 def test_bench_two_independent_sequences():

@@ -80,13 +80,17 @@ def main():
             multi.fused_tile_parallel_icp(eng, dist, n, R, t)
         fused_ms = multi.allreduce_max(dist, (time.perf_counter() - t0) / 5 * 1e3, device=dev)
         fused = dict(valid_fused=okF, iters_fused=stF["iters"], dt_fused=float(np.linalg.norm(t1 - tF)),
+                     R_fused=[float(v) for v in RF.reshape(9)], t_fused=[float(v) for v in tF],
                      dR_fused=float(np.abs(R1 - RF).max()), fused_ms=fused_ms,
                      fused_equals_nccl_bits=bool(np.array_equal(tF, tN) and np.array_equal(RF, RN)))
     out = dict(world=world, n_src=n, valid_single=ok1, valid_tiled=okN, iters_single=st1["iters"],
                iters_tiled=stN["iters"], dt=float(np.linalg.norm(t1 - tN)), dR=float(np.abs(R1 - RN).max()),
                sys_rel=float(np.abs(st1["system"] - stN["system"]).max() / np.abs(st1["system"]).max()),
                inliers_single=float(st1["system"][28]), inliers_tiled=float(stN["system"][28]),
-               single_gpu_ms=one_ms, tiled_ms=tiled_ms, shard=list(stN["shard"]), **fused)
+               single_gpu_ms=one_ms, tiled_ms=tiled_ms, shard=list(stN["shard"]),
+               R_single=[float(v) for v in R1.reshape(9)], t_single=[float(v) for v in t1],
+               R_tiled=[float(v) for v in RN.reshape(9)], t_tiled=[float(v) for v in tN],
+               R_init=[float(v) for v in R.reshape(9)], t_init=[float(v) for v in t], **fused)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
