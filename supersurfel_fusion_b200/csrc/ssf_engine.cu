@@ -1224,7 +1224,9 @@ int ssf_tps_segment(SsfHandle h, const uint8_t* rgb, size_t rgb_stride, const fl
   SSF_CUDA(e, cudaMemcpy2DAsync(e->in_rgb, (size_t)e->W * 3, rgb, rgb_stride, (size_t)e->W * 3, e->H, cudaMemcpyDefault, e->stream));
   SSF_CUDA(e, cudaMemcpy2DAsync(e->in_depth, (size_t)e->W * 4, depth, depth_stride, (size_t)e->W * 4, e->H, cudaMemcpyDefault, e->stream));
   launch_ingest(e, e->in_rgb, (size_t)e->W * 3, e->in_depth, (size_t)e->W * 4);
+  e->pdl_now = (e->tps_trace && getenv("SSF_TPS_TRACE_PDL")) ? e->pdl : 0;   // profiling aid: trace the passes as the frame graph chains them
   launch_tps(e);
+  e->pdl_now = 0;
   SSF_CUDA(e, cudaStreamSynchronize(e->stream));
   SSF_LAUNCH_OK(e);
   if (e->tps_trace) {   // profiling aid: dump the per-CTA phase timestamps of this call

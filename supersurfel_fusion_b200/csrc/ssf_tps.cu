@@ -684,6 +684,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB) tps_pass_tile_kernel(TpsAr
   if (tr) tr[2] = clock64();
   if (TMA) {
     __syncthreads();                       // the barrier was initialised by thread 0: nobody polls it before this
+    if (tr) tr[7] = clock64();
     mbar_wait(&lab_bar, 0);
     // the tensor map fills texels outside the image with 0, a valid label: patch them (border tiles only)
     const bool inside = xs0 >= 0 && xs0 + TILE_COLS <= a.W && y0 - 1 >= 0 && y0 - 1 + TILE_LROWS <= a.H;

@@ -22,5 +22,8 @@ print("CTAs", len(t), "clock 1.965 GHz")
 for k, n in enumerate(names):
     dcy = t[:, k + 1] - t[:, k]
     print("%-40s mean %7.0f cycles (%5.2f us)   max %7.0f" % (n, dcy.mean(), dcy.mean() / 1965.0, dcy.max()))
+if t[:, 7].any():      # stamp between the CTA barrier and the wait for the label tile
+    print("%-40s mean %7.0f cycles" % ("  of which: CTA barrier after the means", (t[:, 7] - t[:, 2]).mean()))
+    print("%-40s mean %7.0f cycles" % ("  of which: wait for the label tile + patch", (t[:, 3] - t[:, 7]).mean()))
 tot = t[:, 6] - t[:, 0]
 print("%-40s mean %7.0f cycles (%5.2f us)   max %7.0f" % ("thread 0, entry to exit", tot.mean(), tot.mean() / 1965.0, tot.max()))
