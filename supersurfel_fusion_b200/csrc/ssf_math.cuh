@@ -19,7 +19,7 @@ namespace ssf {
 // predecessor has completed and its writes are visible).  Both instructions are no-ops for a kernel launched
 // without the attribute (launch_kernel, ssf_engine.h).  Measured on the synchronous VGA frame (SSF_PDL,
 // tools/pdl_ab.sh): a trigger at the TOP of every kernel loses (0.470 vs 0.465 ms: the successor's CTAs take SM
-// slots while the predecessor still needs them), but the 92 fused segmentation passes triggering AFTER their
+// slots while the predecessor still needs them), but the 40 fused segmentation passes of a frame triggering AFTER their
 // decisions and waiting AFTER their argument arithmetic gain 7 % (0.432 ms): that is the default (mode 3).
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
