@@ -27,3 +27,13 @@ if t[:, 7].any():      # stamp between the CTA barrier and the wait for the labe
     print("%-40s mean %7.0f cycles" % ("  of which: wait for the label tile + patch", (t[:, 3] - t[:, 7]).mean()))
 tot = t[:, 6] - t[:, 0]
 print("%-40s mean %7.0f cycles (%5.2f us)   max %7.0f" % ("thread 0, entry to exit", tot.mean(), tot.mean() / 1965.0, tot.max()))
+
+# the pass ends with its slowest CTA: where do the slow ones lose their time?
+order = np.argsort(tot)
+slow = order[-max(1, len(t) // 10):]
+fast = order[:len(t) // 2]
+print("lifetime percentiles (cycles): p50 %.0f  p90 %.0f  p99 %.0f  max %.0f" % tuple(np.percentile(tot, [50, 90, 99, 100])))
+print("%-40s %10s %10s" % ("phase (mean cycles)", "fast half", "slowest 10%"))
+for k, n in enumerate(names):
+    dcy = t[:, k + 1] - t[:, k]
+    print("%-40s %10.0f %10.0f" % (n, dcy[fast].mean(), dcy[slow].mean()))
