@@ -55,3 +55,30 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["gpu_launches"] == 0
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"] == bench.workload_config(1)
+
+
+def test_committed_driver_bench_line_honours_the_contract():
+    """The bench line kept under profiles/ for the round (the driver's own command) carries every key of the
+    bench contract and is self-consistent."""
+    import json
+    path = os.path.join(ROOT, "profiles", "bench_driver_r2_final.json")
+    d = json.loads([l for l in open(path) if l.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] == 5 and d["higher_is_better"] is True
+    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f32"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert abs(d["value"] * d["ms_per_step"] / 1000.0 - 1.0) < 1e-6            # frames/s x s/frame
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 640 * 480 * (3 + 4) and e["d2h_bytes_per_step"] > 0
+    assert e["value"] != d["value"]                                           # measured, not copied
+    assert d["gpu_launches"] >= 57 * d["steps"]
+    c = d["clocks"]
+    assert c["sm_mhz"] > 0.9 * c["sm_max_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(r["achieved"] - 72 * r["n_src"] / (r["us_per_launch"] * 1e-6) / 1e9) < 1e-3 * r["achieved"]
+    assert r["traffic"] and 0.4 < r["dram_frac"] < 1.0
+    b = d["cpu_baseline"]
+    assert b["kind"] in ("port", "reference") and b["cores"] >= 1 and b["value"] > 0 and b["sample"]
